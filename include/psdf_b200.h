@@ -1,0 +1,163 @@
+/*
+ * psdf_b200.h -- C ABI of libpsdf_b200.so, the sm_100a (B200) implementation of PermutoSDF's per-ray
+ * training / sphere-tracing hot path.
+ *
+ * Boundary: the reference exposes this path to Python as a pybind11 module `permuto_sdf`
+ * (src/PyBridge.cxx:30-169) plus the external package `permutohedral_encoding`
+ * (permuto_sdf_py/models/models.py:20,149,186). Both are re-created in Python on top of THIS header
+ * (permuto_sdf_b200/permuto_sdf, permuto_sdf_b200/permutohedral_encoding); every entry point below names
+ * the reference method it replaces. INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers (contiguous, fp32 / int32 / uint8 bool) unless the name ends in
+ *     `[3]` (small host arrays passed by the caller); no allocation happens inside the library;
+ *   - `stream` is a cudaStream_t; kernels are asynchronous on it; the library never synchronises;
+ *   - return value: 0 = ok, <0 = error (PSDF_ERR_*); no global state: RNG state is passed explicitly
+ *     as the (state, inc) pair of a pcg32 generator (kernels/permuto_sdf/pcg32.h:45-171);
+ *   - packed ray containers follow RaySamplesPacked (include/permuto_sdf/RaySamplesPacked.cuh:7-46):
+ *     ray_start_end is int32 [R,2] = [start,end); `equal`/`fixed_n` is the rays_have_equal_nr_of_samples
+ *     fast path; rays with end > max_nr_samples or zero samples are skipped
+ *     (kernels/permuto_sdf/VolumeRenderingGPU.cuh:30-60,103).
+ */
+#ifndef PSDF_B200_H
+#define PSDF_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSDF_ABI_VERSION 1
+#define PSDF_ERR_ARG_ -1
+#define PSDF_ERR_LAUNCH_ -2
+#define PSDF_ERR_UNSUPPORTED_ -3
+
+int psdf_abi_version(void);
+/* 1 when the library was built for sm_100a and a CUDA device is present, else 0 (never a CPU fallback) */
+int psdf_device_ok(void);
+
+/* ---------------------------------------------------------------- Sphere (include/permuto_sdf/Sphere.cuh:12-24) */
+/* Sphere::ray_intersection, src/Sphere.cu:42-79 */
+int psdf_sphere_ray_intersection(int nr_rays, float radius, const float center[3], const float* origins, const float* dirs,
+                                 float* pts_entry, float* t_entry, float* pts_exit, float* t_exit, uint8_t* hit, void* stream);
+/* Sphere::rand_points_inside, src/Sphere.cu:82-109 (random inputs phi,costheta,u are drawn by the caller) */
+int psdf_sphere_rand_points_inside(int n, float radius, const float* phi, const float* costheta, const float* u, float* points,
+                                   void* stream);
+/* Sphere::check_point_inside_primitive, src/Sphere.cu:111-119 */
+int psdf_sphere_check_point_inside(int n, float radius, const float center[3], const float* points, uint8_t* out, void* stream);
+
+/* ---------------------------------------------------------------- OccupancyGrid (include/permuto_sdf/OccupancyGrid.cuh:19-64) */
+/* compute_grid_points (idx==NULL, n==V^3) / compute_random_sample_of_grid_points (idx = chosen voxels),
+ * src/OccupancyGrid.cu:88-117,179-208 */
+int psdf_occ_compute_grid_points(int n, int V, float extent, const float trans[3], const int* idx, uint64_t rng_state,
+                                 uint64_t rng_inc, int randomize, float* out, void* stream);
+/* update_with_density (idx==NULL) / update_with_density_random_sample, src/OccupancyGrid.cu:368-420 */
+int psdf_occ_update_with_density(int n, const float* density, const int* idx, float decay, float thresh, float* values,
+                                 uint8_t* occ, void* stream);
+/* update_with_sdf (idx==NULL, scalar inv_s, variant 0) / update_with_sdf_random_sample (inv_s_dev = 1-element
+ * device tensor, variant 1), src/OccupancyGrid.cu:422-475 */
+int psdf_occ_update_with_sdf(int n, const float* sdf, const int* idx, float extent, int V, float inv_s, const float* inv_s_dev,
+                             float thresh, int random_sample_variant, float* values, uint8_t* occ, void* stream);
+/* check_occupancy, src/OccupancyGrid.cu:339-365 */
+int psdf_occ_check_occupancy(int n, int V, float extent, const float trans[3], const uint8_t* occ, const float* points,
+                             uint8_t* out, void* stream);
+/* compute_samples_in_occupied_regions, src/OccupancyGrid.cu:212-257.
+ * slot_mode 1: ray i owns slots [i*max_per_ray, ...) (deterministic, needs nr_rays*max_per_ray <= max_nr_samples);
+ * slot_mode 0: slots from a global atomic counter like the reference. cur_nr_samples must be zeroed by the caller. */
+int psdf_occ_compute_samples_in_occupied_regions(int nr_rays, int V, float extent, const float trans[3], const float* origins,
+                                                 const float* dirs, const float* t_entry, const float* t_exit,
+                                                 const uint8_t* occ, float min_dist, int max_per_ray, int max_nr_samples,
+                                                 uint64_t rng_state, uint64_t rng_inc, int jitter, int slot_mode,
+                                                 float* s_pos, float* s_dirs, float* s_z, float* s_dt, float* ray_fixed_dt,
+                                                 int* ray_start_end, int* cur_nr_samples, void* stream);
+/* compute_first_sample_start_of_occupied_regions, src/OccupancyGrid.cu:259-300 */
+int psdf_occ_compute_first_sample_start(int nr_rays, int V, float extent, const float trans[3], const float* origins,
+                                        const float* dirs, const float* t_entry, const float* t_exit, const uint8_t* occ,
+                                        int max_nr_samples, int slot_mode, float* s_pos, float* s_dirs, float* s_z, float* s_dt,
+                                        float* ray_fixed_dt, int* ray_start_end, int* cur_nr_samples, void* stream);
+/* advance_sample_to_next_occupied_voxel, src/OccupancyGrid.cu:302-337 (pos updated in place, like the reference) */
+int psdf_occ_advance_sample_to_next_occupied_voxel(int n, int V, float extent, const float trans[3], const float* dirs,
+                                                   float* pos_io, const uint8_t* occ, uint8_t* within, void* stream);
+
+/* ---------------------------------------------------------------- RaySampler (include/permuto_sdf/RaySampler.cuh:21-22) */
+int psdf_sampler_fg(int nr_rays, const float* origins, const float* dirs, const float* t_entry, const float* t_exit,
+                    float min_dist, int max_per_ray, int max_nr_samples, uint64_t rng_state, uint64_t rng_inc, int jitter,
+                    int slot_mode, float* s_pos, float* s_dirs, float* s_z, float* s_dt, float* ray_fixed_dt,
+                    int* ray_start_end, int* cur_nr_samples, void* stream);
+int psdf_sampler_bg(int nr_rays, int n_per_ray, const float* origins, const float* dirs, const float* t_exit,
+                    float sphere_radius, const float sphere_center[3], uint64_t rng_state, uint64_t rng_inc, int randomize,
+                    int contract, float* s3, float* s4, float* s_dirs, float* s_z, float* s_dt, float* ray_fixed_dt,
+                    int* ray_start_end, void* stream);
+
+/* ---------------------------------------------------------------- RaySamplesPacked (src/RaySamplesPacked.cu:44-146) */
+long long psdf_packed_compact_workspace_bytes(int nr_rays);
+/* compute_exact_nr_samples without the host sync: total_dev <- sum(end-start) */
+int psdf_packed_count_samples(int nr_rays, const int* ray_start_end, int* total_dev, void* stream);
+/* compact_to_valid_samples = scan (fills workspace; workspace[nr_rays + nblocks] is the total) + copy */
+int psdf_packed_compact_scan(int nr_rays, const int* ray_start_end, int* workspace, void* stream);
+int psdf_packed_compact_copy(int nr_rays, const float* pos, const float* pos4, const float* dirs, const float* z,
+                             const float* dt, const float* sdf, const float* fixed_dt, const int* ray_start_end,
+                             const int* workspace, float* o_pos, float* o_pos4, float* o_dirs, float* o_z, float* o_dt,
+                             float* o_sdf, float* o_fixed_dt, int* o_start_end, void* stream);
+/* compute_per_sample_ray_idx */
+int psdf_packed_per_sample_ray_idx(int nr_rays, int nr_samples, const int* ray_start_end, int* out, void* stream);
+
+/* ---------------------------------------------------------------- VolumeRendering (include/permuto_sdf/VolumeRendering.cuh:22-38) */
+#define PSDF_RSP int nr_rays, int max_nr_samples, const int* ray_start_end, int equal, int fixed_n
+int psdf_vr_cumprod_alpha2transmittance(PSDF_RSP, const float* one_minus_alpha, float* transmittance, float* bg_transmittance, void* stream);
+int psdf_vr_integrate_with_weights(PSDF_RSP, const float* vals, const float* weights, float* out, void* stream);
+int psdf_vr_sdf2alpha(PSDF_RSP, const float* ray_fixed_dt, const float* samples_dt, const float* sdf, float inv_s, int dynamic_inv_s,
+                      float inv_s_multiplier, float* alpha, void* stream);
+int psdf_vr_sum_over_each_ray(PSDF_RSP, int val_dim, const float* vals, float* sum_ray, float* sum_sample, void* stream);
+int psdf_vr_cumsum_over_each_ray(PSDF_RSP, const float* vals, int inverse, float* out, void* stream);
+int psdf_vr_compute_cdf(PSDF_RSP, const float* weights, float* cdf, void* stream);
+int psdf_vr_importance_sample(PSDF_RSP, const float* origins, const float* dirs, const float* ray_fixed_dt, const float* samples_z,
+                              const float* cdf, int nr_imp, uint64_t rng_state, uint64_t rng_inc, int jitter, float* o_pos,
+                              float* o_dirs, float* o_z, void* stream);
+long long psdf_vr_combine_workspace_bytes(int nr_rays);
+int psdf_vr_combine_uniform_samples_with_imp(PSDF_RSP, const float* origins, const float* dirs, const float* t_exit,
+                                             const float* u_fixed_dt, const float* u_z, const float* u_sdf, int u_has_sdf,
+                                             int imp_n, const float* i_z, const float* i_sdf, int i_has_sdf, int c_max,
+                                             int* workspace, float* c_pos, float* c_dirs, float* c_z, float* c_dt, float* c_sdf,
+                                             float* c_fixed_dt, int* c_start_end, void* stream);
+int psdf_vr_cumprod_alpha2transmittance_backward(PSDF_RSP, const float* grad_bg_transmittance, const float* alpha,
+                                                 const float* bg_transmittance, const float* cumsumLV, float* grad_alpha,
+                                                 void* stream);
+int psdf_vr_integrate_with_weights_backward(PSDF_RSP, const float* grad_pred, const float* vals, const float* weights,
+                                            int reference_bug, float* grad_vals, float* grad_weights, void* stream);
+int psdf_vr_sum_over_each_ray_backward(PSDF_RSP, int val_dim, const float* grad_sum_ray, const float* grad_sum_sample,
+                                       float* grad_vals, void* stream);
+int psdf_vr_compute_dt(PSDF_RSP, int use_t_exit, const float* t_exit, const float* samples_z, float* dt, void* stream);
+int psdf_vr_volume_render_nerf(PSDF_RSP, const float* rgb, const float* radiance, const float* samples_z, const float* samples_dt,
+                               float* pred_rgb, float* pred_depth, float* bg_transmittance, float* weight_per_sample, void* stream);
+int psdf_vr_volume_render_nerf_backward(PSDF_RSP, const float* grad_pred_rgb, const float* grad_bg_transmittance,
+                                        const float* pred_rgb, const float* bg_transmittance, const float* rgb,
+                                        const float* radiance, const float* samples_dt, float* grad_rgb, float* grad_radiance,
+                                        void* stream);
+
+/* ---------------------------------------------------------------- PermutoSDF statics (include/permuto_sdf/PermutoSDF.cuh:46-55) */
+int psdf_spherical_harmonics(int n, int degree, const float* dirs, float* out, void* stream);
+int psdf_random_rays_from_reel(int nr_rays, int nr_images, int H, int W, const float* rgb_reel, const float* mask_reel,
+                               const float* K, const float* tf_world_cam, const int* pixel_indices, const int* img_indices,
+                               int has_mask, float* origins, float* dirs, float* gt_rgb, float* gt_mask, void* stream);
+
+/* ---------------------------------------------------------------- permutohedral_encoding (external package; call sites
+ * permuto_sdf_py/models/models.py:149,186; semantics SURVEY.md Appendix B)
+ * pos [N,D] fp32, lattice [L,T,F] fp32, scale_factor [L,D], shift [L,D], window [L];
+ * out [N,(L+E)*F] with E=ceil(D/F) concat columns when concat_points. D in {3,4}, F == 2. */
+int psdf_enc_forward(int N, int D, int L, int F, int T, const float* pos, const float* lattice, const float* scale_factor,
+                     const float* shift, const float* window, int concat_points, float points_scaling, float* out, void* stream);
+/* grad wrt lattice (+=, caller zeroes) and/or positions (=) from grad_out [N,(L+E)*F]; either output may be NULL */
+int psdf_enc_backward(int N, int D, int L, int F, int T, const float* pos, const float* lattice, const float* scale_factor,
+                      const float* shift, const float* window, int concat_points, float points_scaling, const float* grad_out,
+                      float* grad_lattice, float* grad_pos, void* stream);
+/* double backward from the positions gradient: given gg_pos [N,D] (grad of grad_pos) produce
+ * grad_lattice (+=) and grad_grad_out [N,(L+E)*F] (=); either may be NULL */
+int psdf_enc_double_backward(int N, int D, int L, int F, int T, const float* pos, const float* lattice, const float* scale_factor,
+                             const float* shift, const float* window, int concat_points, float points_scaling,
+                             const float* gg_pos, const float* grad_out, float* grad_lattice, float* grad_grad_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

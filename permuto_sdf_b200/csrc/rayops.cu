@@ -1,0 +1,853 @@
+// Ray-path kernels for sm_100a: bounding sphere, occupancy grid (Morton DDA), packed sample
+// containers, fg/bg ray samplers, spherical harmonics and ray generation.
+// Compiled with -fmad=false: every FMA below is explicit and placed where the reference's nvcc build
+// contracts (see common.cuh). Reference semantics cited per kernel.
+//
+// Work mapping (B200): DDA marchers are one thread per ray because the voxel walk is a serial
+// float recurrence (t += step + eps) that must be reproduced bit-for-bit; the occupancy bytes they need
+// do not feed the recurrence, so they are fetched in batches of kBatch independent loads (L2-resident
+// 16.8 MB grid) instead of one dependent load per step. Copy/packing kernels are warp-per-ray with
+// coalesced accesses. Slots in the sample pool are deterministic (ray * stride) rather than handed out
+// by a global atomic, with the reference's atomic order available as slot_mode=0.
+#include "common.cuh"
+#include "../../include/psdf_b200.h"
+
+using namespace psdf;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxSteps = 4096;  // OccupancyGridGPU.cuh:24
+constexpr int kBatch = 8;
+
+// ------------------------------------------------------------------------------------------------ Sphere
+// SphereGPU.cuh:21-93. FMA placement copied from the reference SASS: dot(a,b)=fma(az,bz,fma(ax,bx,ay*by)).
+__global__ void __launch_bounds__(kThreads) k_sphere_ray_intersection(int n, float radius, float cx, float cy, float cz,
+                                                                      const float* __restrict__ origins,
+                                                                      const float* __restrict__ dirs, float* __restrict__ pe,
+                                                                      float* __restrict__ te, float* __restrict__ px,
+                                                                      float* __restrict__ tx, uint8_t* __restrict__ hit) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float ox = origins[3 * i], oy = origins[3 * i + 1], oz = origins[3 * i + 2];
+    float dx = dirs[3 * i], dy = dirs[3 * i + 1], dz = dirs[3 * i + 2];
+    float qx = __fsub_rn(ox, cx), qy = __fsub_rn(oy, cy), qz = __fsub_rn(oz, cz);
+    float a = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+    float bh = __fmaf_rn(dz, qz, __fmaf_rn(dx, qx, __fmul_rn(dy, qy)));
+    float b = __fadd_rn(bh, bh);
+    float c = __fmaf_rn(-radius, radius, __fmaf_rn(qz, qz, __fmaf_rn(qx, qx, __fmul_rn(qy, qy))));
+    float disc = __fmaf_rn(b, b, __fmul_rn(__fmul_rn(a, -4.0f), c));
+    float sq = __fsqrt_rn(fabsf(disc));
+    double den = 2.0 * (double)a;
+    float t0 = (float)((double)__fsub_rn(-b, sq) / den);
+    float t1 = (float)((double)__fadd_rn(-b, sq) / den);
+    bool miss = disc < 0.0f;
+    if (miss) { t0 = 0.0f; t1 = 0.0f; }
+    t0 = fmaxf(0.0f, t0);
+    pe[3 * i] = __fmaf_rn(dx, t0, ox); pe[3 * i + 1] = __fmaf_rn(dy, t0, oy); pe[3 * i + 2] = __fmaf_rn(dz, t0, oz);
+    px[3 * i] = __fmaf_rn(dx, t1, ox); px[3 * i + 1] = __fmaf_rn(dy, t1, oy); px[3 * i + 2] = __fmaf_rn(dz, t1, oz);
+    te[i] = t0;
+    tx[i] = t1;
+    hit[i] = miss ? 0 : 1;
+}
+// SphereGPU.cuh:96-130 (the centre is not added, like the reference)
+__global__ void __launch_bounds__(kThreads) k_sphere_rand_points(int n, float radius, const float* __restrict__ phi,
+                                                                 const float* __restrict__ ct, const float* __restrict__ u,
+                                                                 float* __restrict__ pts) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float theta = acosf(ct[i]);
+    float r = radius * (float)pow((double)u[i], 1.0 / 3);
+    float st = sinf(theta);
+    pts[3 * i] = r * st * cosf(phi[i]);
+    pts[3 * i + 1] = r * st * sinf(phi[i]);
+    pts[3 * i + 2] = r * cosf(theta);
+}
+// Sphere.cu:111-119 : ||p - c|| < radius
+__global__ void __launch_bounds__(kThreads) k_sphere_inside(int n, float radius, float cx, float cy, float cz,
+                                                            const float* __restrict__ p, uint8_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x = p[3 * i] - cx, y = p[3 * i + 1] - cy, z = p[3 * i + 2] - cz;
+    out[i] = sqrtf(x * x + y * y + z * z) < radius;
+}
+
+// ------------------------------------------------------------------------------------------------ Occupancy
+// OccupancyGridGPU.cuh:196-301
+__global__ void __launch_bounds__(kThreads) k_occ_grid_points(int n, GridGeom g, const int* __restrict__ idx, Pcg32 rng,
+                                                              bool randomize, float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t v = idx ? (uint32_t)idx[i] : (uint32_t)i;
+    float3 p = voxel_to_pos(v, g, true);
+    if (randomize) {
+        float vs = __fdiv_rn(g.extent, (float)g.V);
+        float half = __fmul_rn(vs, 0.5f);
+        rng.advance((int64_t)(i * 3));
+        p.x = __fadd_rn(p.x, __fmaf_rn(rng.next_float(), vs, -half));
+        p.y = __fadd_rn(p.y, __fmaf_rn(rng.next_float(), vs, -half));
+        p.z = __fadd_rn(p.z, __fmaf_rn(rng.next_float(), vs, -half));
+    }
+    out[3 * i] = p.x; out[3 * i + 1] = p.y; out[3 * i + 2] = p.z;
+}
+// OccupancyGridGPU.cuh:303-378
+__global__ void __launch_bounds__(kThreads) k_occ_update_density(int n, const float* __restrict__ density,
+                                                                 const int* __restrict__ idx, float decay, float thresh,
+                                                                 float* __restrict__ values, uint8_t* __restrict__ occ) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = idx ? idx[i] : i;
+    float upd = fmaxf(density[i], __fmul_rn(values[v], decay));
+    values[v] = upd;
+    occ[v] = upd > thresh;
+}
+// OccupancyGridGPU.cuh:381-507 ; logistic pdf s*e/(1+e)^2 with e=exp(-s*x)
+__global__ void __launch_bounds__(kThreads) k_occ_update_sdf(int n, const float* __restrict__ sdf, const int* __restrict__ idx,
+                                                             float range, float inv_s_scalar,
+                                                             const float* __restrict__ inv_s_dev, float thresh,
+                                                             float* __restrict__ values, uint8_t* __restrict__ occ) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int v = idx ? idx[i] : i;
+    float s = sdf[i];
+    values[v] = s;
+    float inv_s = inv_s_dev ? inv_s_dev[0] : inv_s_scalar;
+    float capped = clampf(fabsf(s) - range, 0.0f, 1e10f);
+    float e = expf(-inv_s * capped);
+    float w = inv_s * e / powf(1.0f + e, 2.0f);
+    occ[v] = w > thresh;
+}
+// OccupancyGridGPU.cuh:901-941
+__global__ void __launch_bounds__(kThreads) k_occ_check(int n, GridGeom g, const uint8_t* __restrict__ occ,
+                                                        const float* __restrict__ pts, uint8_t* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int nv = g.V * g.V * g.V;
+    int v = pos_to_voxel(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], g);
+    bool oob = v > (nv - 1) || v < 0;
+    out[i] = oob ? 0 : occ[v];
+}
+
+struct RayIn {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
+};
+__device__ __forceinline__ RayIn load_ray(const float* __restrict__ origins, const float* __restrict__ dirs, int i) {
+    RayIn r;
+    r.ox = origins[3 * i]; r.oy = origins[3 * i + 1]; r.oz = origins[3 * i + 2];
+    r.dx = dirs[3 * i]; r.dy = dirs[3 * i + 1]; r.dz = dirs[3 * i + 2];
+    r.ix = safe_inv(r.dx); r.iy = safe_inv(r.dy); r.iz = safe_inv(r.dz);
+    return r;
+}
+
+// OccupancyGridGPU.cuh:510-703
+// slot_mode 1: ray i owns slots [i*max_per_ray, (i+1)*max_per_ray) (deterministic); 0: global atomic like the reference.
+__global__ void __launch_bounds__(kThreads)
+k_occ_samples_in_occupied(int nr_rays, GridGeom g, const float* __restrict__ origins, const float* __restrict__ dirs,
+                          const float* __restrict__ t_entry, const float* __restrict__ t_exit_,
+                          const uint8_t* __restrict__ occ, float min_dist, int max_per_ray, int max_nr_samples, Pcg32 rng,
+                          bool jitter, int slot_mode, float* __restrict__ s_pos, float* __restrict__ s_dirs,
+                          float* __restrict__ s_z, float* __restrict__ s_dt, float* __restrict__ ray_fixed_dt,
+                          int* __restrict__ start_end, int* __restrict__ cur_nr_samples) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nr_rays) return;
+    const int nv = g.V * g.V * g.V;
+    const float eps = 1e-6f;
+    RayIn r = load_ray(origins, dirs, idx);
+    float t_start = t_entry[idx], t_exit = t_exit_[idx];
+
+    // ---- pass 1: length of the ray inside occupied voxels. The t recurrence runs kBatch steps ahead of the
+    // occupancy loads so each batch costs one L2 latency instead of kBatch.
+    float t = t_start;
+    int steps = 0;
+    float occ_len = 0.0f;
+    bool alive = (t < t_exit);
+    while (alive) {
+        int vb[kBatch];
+        float dnb[kBatch], tb[kBatch];
+        int m = 0;
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            if (alive) {
+                float px = __fmaf_rn(r.dx, t, r.ox), py = __fmaf_rn(r.dy, t, r.oy), pz = __fmaf_rn(r.dz, t, r.oz);
+                int v = pos_to_voxel(px, py, pz, g);
+                if (v >= nv || v < 0) { alive = false; }
+                else {
+                    float dn = dda_step(px, py, pz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, g.V);
+                    t = __fadd_rn(__fadd_rn(t, dn), eps);
+                    vb[k] = v; dnb[k] = dn; tb[k] = t;
+                    m = k + 1;
+                    steps++;
+                    alive = (t < t_exit) && (steps < kMaxSteps);
+                }
+            }
+        }
+        uint8_t ob[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) ob[k] = (k < m) ? __ldg(occ + vb[k]) : 0;
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) {
+            if (k < m && ob[k]) {
+                occ_len = __fadd_rn(occ_len, dnb[k]);
+                float tm = __fsub_rn(tb[k], eps);
+                if (tm > t_exit) occ_len = __fsub_rn(occ_len, __fsub_rn(tm, t_exit));
+            }
+        }
+    }
+
+    int n_create = (int)__fdiv_rn(occ_len, min_dist);
+    n_create = min(max(n_create, 0), max_per_ray);
+    float spacing = __fdiv_rn(occ_len, (float)n_create);
+
+    if (n_create > 1) {
+        int start;
+        if (slot_mode == 1) { start = idx * max_per_ray; atomicAdd(cur_nr_samples, n_create); }
+        else start = atomicAdd(cur_nr_samples, n_create);
+        start_end[2 * idx] = start;
+        start_end[2 * idx + 1] = start + n_create;
+        ray_fixed_dt[idx] = spacing;
+        if (start + n_create > max_nr_samples) return;
+
+        t = t_start;
+        steps = 0;
+        if (jitter) {
+            rng.advance(idx);
+            t = __fmaf_rn(rng.next_float(), spacing, t);
+        }
+        int created = 0;
+        float last_z = 0.0f;
+        while (t < t_exit && steps < kMaxSteps) {
+            t = clampf(t, t_start, t_exit);
+            float px = __fmaf_rn(r.dx, t, r.ox), py = __fmaf_rn(r.dy, t, r.oy), pz = __fmaf_rn(r.dz, t, r.oz);
+            int v = pos_to_voxel(px, py, pz, g);
+            if (v >= nv || v < 0) break;
+            if (__ldg(occ + v) && created < n_create) {
+                int s = start + created;
+                s_pos[3 * s] = px; s_pos[3 * s + 1] = py; s_pos[3 * s + 2] = pz;
+                s_dirs[3 * s] = r.dx; s_dirs[3 * s + 1] = r.dy; s_dirs[3 * s + 2] = r.dz;
+                s_z[s] = t;
+                s_dt[s] = spacing;
+                last_z = t;
+                t = __fadd_rn(t, spacing);
+                created++;
+            } else {
+                float delta = dda_step(px, py, pz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, g.V);
+                if (jitter) delta = __fmaf_rn(rng.next_float(), spacing, delta);
+                t = __fadd_rn(__fadd_rn(t, delta), eps);
+            }
+            steps++;
+        }
+        if (created > 0) s_dt[start + created - 1] = clampf(__fsub_rn(t_exit, last_z), 0.0f, spacing);
+        for (int i = created; i < n_create; i++) {
+            int s = start + i;
+            s_pos[3 * s] = 0; s_pos[3 * s + 1] = 0; s_pos[3 * s + 2] = 0;
+            s_dirs[3 * s] = 0; s_dirs[3 * s + 1] = 0; s_dirs[3 * s + 2] = 0;
+            s_z[s] = -1.0f;
+            s_dt[s] = 0;
+        }
+        start_end[2 * idx + 1] = start + created;
+        if (created <= 2) {
+            ray_fixed_dt[idx] = 0;
+            start_end[2 * idx] = 0;
+            start_end[2 * idx + 1] = 0;
+        }
+    } else {
+        ray_fixed_dt[idx] = 0;
+        start_end[2 * idx] = 0;
+        start_end[2 * idx + 1] = 0;
+    }
+}
+
+// OccupancyGridGPU.cuh:707-814 ; one sample at the first occupied voxel. slot_mode 1: slot == ray index.
+__global__ void __launch_bounds__(kThreads)
+k_occ_first_sample(int nr_rays, GridGeom g, const float* __restrict__ origins, const float* __restrict__ dirs,
+                   const float* __restrict__ t_entry, const float* __restrict__ t_exit_, const uint8_t* __restrict__ occ,
+                   int max_nr_samples, int slot_mode, float* __restrict__ s_pos, float* __restrict__ s_dirs,
+                   float* __restrict__ s_z, float* __restrict__ s_dt, float* __restrict__ ray_fixed_dt,
+                   int* __restrict__ start_end, int* __restrict__ cur_nr_samples) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nr_rays) return;
+    const int nv = g.V * g.V * g.V;
+    const float eps = 1e-6f;
+    RayIn r = load_ray(origins, dirs, idx);
+    float t = t_entry[idx], t_exit = t_exit_[idx];
+    // the reference loop never increments nr_steps (:759-798); t grows by >= eps per step so it ends.
+    while (t < t_exit) {
+        float px = __fmaf_rn(r.dx, t, r.ox), py = __fmaf_rn(r.dy, t, r.oy), pz = __fmaf_rn(r.dz, t, r.oz);
+        int v = pos_to_voxel(px, py, pz, g);
+        if (v >= nv || v < 0) break;
+        float dn = dda_step(px, py, pz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, g.V);
+        t = __fadd_rn(__fadd_rn(t, dn), eps);
+        if (__ldg(occ + v)) {
+            int start;
+            if (slot_mode == 1) { start = idx; atomicAdd(cur_nr_samples, 1); }
+            else start = atomicAdd(cur_nr_samples, 1);
+            start_end[2 * idx] = start;
+            start_end[2 * idx + 1] = start + 1;
+            ray_fixed_dt[idx] = 0;
+            if (start + 1 > max_nr_samples) return;
+            s_pos[3 * start] = px; s_pos[3 * start + 1] = py; s_pos[3 * start + 2] = pz;
+            s_dirs[3 * start] = r.dx; s_dirs[3 * start + 1] = r.dy; s_dirs[3 * start + 2] = r.dz;
+            s_z[start] = t;  // already advanced t, as in the reference (:766,790)
+            s_dt[start] = 0;
+            return;
+        }
+    }
+    ray_fixed_dt[idx] = 0;
+    start_end[2 * idx] = 0;
+    start_end[2 * idx + 1] = 0;
+}
+
+// OccupancyGridGPU.cuh:817-895 ; in-place update of pos (output aliases input, OccupancyGrid.cu:311)
+__global__ void __launch_bounds__(kThreads)
+k_occ_advance_to_next_occupied(int n, GridGeom g, const float* __restrict__ dirs, float* __restrict__ pos_io,
+                               const uint8_t* __restrict__ occ, uint8_t* __restrict__ within) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int nv = g.V * g.V * g.V;
+    const float eps = 1e-6f;
+    RayIn r = load_ray(pos_io, dirs, idx);
+    const double max_steps = (double)g.V * sqrt(3.0);
+    float t = 0;
+    int steps = 0;
+    bool wb = true;
+    while (wb && (double)steps < max_steps) {
+        float px = __fmaf_rn(r.dx, t, r.ox), py = __fmaf_rn(r.dy, t, r.oy), pz = __fmaf_rn(r.dz, t, r.oz);
+        int v = pos_to_voxel(px, py, pz, g);
+        bool oob = v > (nv - 1) || v < 0;
+        if (oob) {
+            wb = false;
+            pos_io[3 * idx] = px; pos_io[3 * idx + 1] = py; pos_io[3 * idx + 2] = pz;
+            break;
+        }
+        float dn = dda_step(px, py, pz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, g.V);
+        t = __fadd_rn(__fadd_rn(t, dn), eps);
+        if (__ldg(occ + v)) {
+            pos_io[3 * idx] = px; pos_io[3 * idx + 1] = py; pos_io[3 * idx + 2] = pz;
+            break;
+        }
+        steps++;
+    }
+    within[idx] = wb ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------ RaySampler
+// RaySamplerGPU.cuh:162-335
+__global__ void __launch_bounds__(kThreads)
+k_sampler_fg(int nr_rays, const float* __restrict__ origins, const float* __restrict__ dirs, const float* __restrict__ t_entry,
+             const float* __restrict__ t_exit_, float min_dist, int max_per_ray, int max_nr_samples, Pcg32 rng, bool jitter,
+             int slot_mode, float* __restrict__ s_pos, float* __restrict__ s_dirs, float* __restrict__ s_z,
+             float* __restrict__ s_dt, float* __restrict__ ray_fixed_dt, int* __restrict__ start_end,
+             int* __restrict__ cur_nr_samples) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nr_rays) return;
+    const float eps = 1e-6f;
+    float ox = origins[3 * idx], oy = origins[3 * idx + 1], oz = origins[3 * idx + 2];
+    float dx = dirs[3 * idx], dy = dirs[3 * idx + 1], dz = dirs[3 * idx + 2];
+    float t_start = t_entry[idx], t_exit = t_exit_[idx];
+    float len = __fsub_rn(t_exit, t_start);
+    int n_create = (int)__fdiv_rn(len, min_dist);
+    n_create = min(max(n_create, 0), max_per_ray);
+    float spacing = __fdiv_rn(len, (float)n_create);
+    if (n_create > 1 && len > eps) {
+        int start;
+        if (slot_mode == 1) { start = idx * max_per_ray; atomicAdd(cur_nr_samples, n_create); }
+        else start = atomicAdd(cur_nr_samples, n_create);
+        start_end[2 * idx] = start;
+        start_end[2 * idx + 1] = start + n_create;
+        ray_fixed_dt[idx] = spacing;
+        if (start + n_create > max_nr_samples) return;
+        float t = t_start;
+        int steps = 0;
+        if (jitter) {
+            rng.advance(idx);
+            t = __fmaf_rn(rng.next_float(), spacing, t);
+        }
+        int created = 0;
+        float last_z = 0;
+        while (t < t_exit && steps < kMaxSteps) {
+            t = clampf(t, t_start, t_exit);
+            if (created < n_create) {
+                int s = start + created;
+                s_pos[3 * s] = __fmaf_rn(dx, t, ox); s_pos[3 * s + 1] = __fmaf_rn(dy, t, oy); s_pos[3 * s + 2] = __fmaf_rn(dz, t, oz);
+                s_dirs[3 * s] = dx; s_dirs[3 * s + 1] = dy; s_dirs[3 * s + 2] = dz;
+                s_z[s] = t;
+                s_dt[s] = spacing;
+                last_z = t;
+                t = __fadd_rn(t, spacing);
+                created++;
+            }
+            steps++;
+        }
+        if (created > 0) s_dt[start + created - 1] = clampf(__fsub_rn(t_exit, last_z), 0.0f, spacing);
+        for (int i = created; i < n_create; i++) {
+            int s = start + i;
+            s_pos[3 * s] = 0; s_pos[3 * s + 1] = 0; s_pos[3 * s + 2] = 0;
+            s_dirs[3 * s] = 0; s_dirs[3 * s + 1] = 0; s_dirs[3 * s + 2] = 0;
+            s_z[s] = -1.0f;
+            s_dt[s] = 0;
+        }
+        start_end[2 * idx + 1] = start + created;
+        if (created <= 2) {
+            ray_fixed_dt[idx] = 0;
+            start_end[2 * idx] = 0;
+            start_end[2 * idx + 1] = 0;
+        }
+    } else {
+        ray_fixed_dt[idx] = 0;
+        start_end[2 * idx] = 0;
+        start_end[2 * idx + 1] = 0;
+    }
+}
+
+// RaySamplerGPU.cuh:37-158 ; inverse-depth background samples with the NeRF++ 4-D parametrisation.
+// The per-sample cumulative rng.advance(idx*n) of the reference (:88-94) is kept.
+__global__ void __launch_bounds__(kThreads)
+k_sampler_bg(int nr_rays, int n_per_ray, const float* __restrict__ origins, const float* __restrict__ dirs,
+             const float* __restrict__ t_exit_, float sphere_radius, float cx, float cy, float cz, Pcg32 rng, bool randomize,
+             bool contract, float* __restrict__ s3, float* __restrict__ s4, float* __restrict__ s_dirs,
+             float* __restrict__ s_z, float* __restrict__ s_dt, float* __restrict__ ray_fixed_dt,
+             int* __restrict__ start_end) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nr_rays) return;
+    float ox = origins[3 * idx], oy = origins[3 * idx + 1], oz = origins[3 * idx + 2];
+    float dx = dirs[3 * idx], dy = dirs[3 * idx + 1], dz = dirs[3 * idx + 2];
+    float t_exit = t_exit_[idx];
+    const float min_t = 1e-3f;
+    float t_between = (float)((1.0 - (double)min_t) / (double)(n_per_ray - 1));
+    float prev_z = 0;
+    for (int i = 0; i < n_per_ray; i++) {
+        float t_sample = (float)(1.0 - (double)__fmul_rn((float)i, t_between));
+        if (randomize) {
+            rng.advance((int64_t)(idx * n_per_ray));
+            float rnd = rng.next_float();
+            float mov = (float)((double)__fmul_rn(t_between, rnd) - (double)t_between / 2.0);
+            t_sample = __fadd_rn(t_sample, mov);
+        }
+        t_sample = clampf(t_sample, min_t, 1.0f);
+        float z = __fdiv_rn(t_exit, t_sample);
+        int s = idx * n_per_ray + i;
+        s_z[s] = z;
+        if (i > 0) s_dt[s - 1] = __fsub_rn(z, prev_z);
+        prev_z = z;
+        float px = __fmaf_rn(z, dx, ox), py = __fmaf_rn(z, dy, oy), pz = __fmaf_rn(z, dz, oz);
+        if (contract) {
+            float tr = t_sample * sphere_radius;
+            float len = sqrtf(px * px + py * py + pz * pz);
+            float f = 2 * sphere_radius - tr;
+            px = f * (px / len); py = f * (py / len); pz = f * (pz / len);
+        }
+        s3[3 * s] = px; s3[3 * s + 1] = py; s3[3 * s + 2] = pz;
+        float qx = px - cx, qy = py - cy, qz = pz - cz;
+        float d2 = qx * qx + qy * qy + qz * qz;
+        float inv = rsqrtf(d2);
+        float dist = sqrtf(d2);
+        s4[4 * s] = qx * inv; s4[4 * s + 1] = qy * inv; s4[4 * s + 2] = qz * inv;
+        s4[4 * s + 3] = sphere_radius / fmaxf(1e-6f, dist);
+        s_dirs[3 * s] = dx; s_dirs[3 * s + 1] = dy; s_dirs[3 * s + 2] = dz;
+    }
+    s_dt[idx * n_per_ray + n_per_ray - 1] = 1e10f;
+    ray_fixed_dt[idx] = 0;
+    start_end[2 * idx] = idx * n_per_ray;
+    start_end[2 * idx + 1] = idx * n_per_ray + n_per_ray;
+}
+
+// ------------------------------------------------------------------------------------------------ Packed container
+// Deterministic compaction = exclusive scan of per-ray counts + warp-per-ray coalesced copy
+// (replaces the atomic slot grab + serial per-thread copy of RaySamplesPackedGPU.cuh:15-81).
+constexpr int kScanThreads = 1024;
+__device__ __forceinline__ int block_inclusive_scan(int v, int* smem /* 32 ints */) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane == 31) smem[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        int s = smem[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        smem[lane] = s;
+    }
+    __syncthreads();
+    if (w > 0) v += smem[w - 1];
+    __syncthreads();
+    return v;
+}
+// stage A: per-block scan of counts; writes exclusive offsets (block-local) and block totals
+__global__ void __launch_bounds__(kScanThreads) k_scan_counts_local(int nr_rays, const int* __restrict__ start_end,
+                                                                    int* __restrict__ offsets, int* __restrict__ block_sums) {
+    __shared__ int sm[32];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0;
+    if (i < nr_rays) { int2 se = reinterpret_cast<const int2*>(start_end)[i]; c = se.y - se.x; }
+    int inc = block_inclusive_scan(c, sm);
+    if (i < nr_rays) offsets[i] = inc - c;
+    if (threadIdx.x == blockDim.x - 1) block_sums[blockIdx.x] = inc;
+}
+// stage B: one block scans the block totals in place (exclusive) and writes the grand total
+__global__ void __launch_bounds__(kScanThreads) k_scan_block_sums(int nblocks, int* __restrict__ block_sums,
+                                                                  int* __restrict__ total) {
+    __shared__ int sm[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int c = i < nblocks ? block_sums[i] : 0;
+        int inc = block_inclusive_scan(c, sm);
+        int cr = carry;
+        if (i < nblocks) block_sums[i] = cr + inc - c;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = cr + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+// stage C: warp per ray, coalesced copy of every per-sample array
+__global__ void __launch_bounds__(kThreads)
+k_compact_copy(int nr_rays, const float* __restrict__ pos, const float* __restrict__ pos4, const float* __restrict__ dirs,
+               const float* __restrict__ z, const float* __restrict__ dt, const float* __restrict__ sdf,
+               const float* __restrict__ fixed_dt, const int* __restrict__ start_end, const int* __restrict__ offsets,
+               const int* __restrict__ block_sums, float* __restrict__ o_pos, float* __restrict__ o_pos4,
+               float* __restrict__ o_dirs, float* __restrict__ o_z, float* __restrict__ o_dt, float* __restrict__ o_sdf,
+               float* __restrict__ o_fixed_dt, int* __restrict__ o_start_end) {
+    int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (ray >= nr_rays) return;
+    int2 se = reinterpret_cast<const int2*>(start_end)[ray];
+    int n = se.y - se.x;
+    int os = offsets[ray] + block_sums[ray / kScanThreads];
+    if (lane == 0) {
+        o_fixed_dt[ray] = fixed_dt[ray];
+        reinterpret_cast<int2*>(o_start_end)[ray] = make_int2(os, os + n);
+    }
+    for (int i = lane; i < 3 * n; i += 32) {
+        o_pos[3 * os + i] = pos[3 * se.x + i];
+        o_dirs[3 * os + i] = dirs[3 * se.x + i];
+    }
+    if (pos4) for (int i = lane; i < 4 * n; i += 32) o_pos4[4 * os + i] = pos4[4 * se.x + i];
+    for (int i = lane; i < n; i += 32) {
+        o_z[os + i] = z[se.x + i];
+        o_dt[os + i] = dt[se.x + i];
+        if (sdf) o_sdf[os + i] = sdf[se.x + i];
+    }
+}
+// sum over rays of (end-start) -> device int (RaySamplesPacked.cu:44-55 without the host sync)
+__global__ void __launch_bounds__(kScanThreads) k_count_samples(int nr_rays, const int* __restrict__ start_end,
+                                                                int* __restrict__ total) {
+    __shared__ int sm[32];
+    int acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nr_rays; i += gridDim.x * blockDim.x) {
+        int2 se = reinterpret_cast<const int2*>(start_end)[i];
+        acc += se.y - se.x;
+    }
+    int inc = block_inclusive_scan(acc, sm);
+    if (threadIdx.x == blockDim.x - 1 && inc) atomicAdd(total, inc);
+}
+// RaySamplesPackedGPU.cuh:84-115, warp per ray
+__global__ void __launch_bounds__(kThreads) k_per_sample_ray_idx(int nr_rays, int nr_samples, const int* __restrict__ start_end,
+                                                                 int* __restrict__ out) {
+    int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (ray >= nr_rays) return;
+    int2 se = reinterpret_cast<const int2*>(start_end)[ray];
+    for (int i = se.x + lane; i < se.y; i += 32)
+        if (i < nr_samples) out[i] = ray;
+}
+
+// ------------------------------------------------------------------------------------------------ SH + ray generation
+// Real spherical harmonics up to degree 7 (PermutoSDFGPU.cuh:275-365). Channel c of sample i is evaluated by thread
+// (i, c-group): the polynomial table is the standard one; outputs are written as a coalesced [N, degree^2] block.
+__device__ __forceinline__ void sh_eval(float x, float y, float z, int degree, float* o) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;
+    if (degree <= 1) return;
+    const float c1 = 0.48860251190291987f;
+    o[1] = -c1 * y; o[2] = c1 * z; o[3] = -c1 * x;
+    if (degree <= 2) return;
+    const float c2 = 1.0925484305920792f;
+    o[4] = c2 * xy; o[5] = -c2 * yz; o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f; o[7] = -c2 * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    if (degree <= 3) return;
+    const float c3a = 0.59004358992664352f, c3b = 0.45704579946446572f;
+    o[9] = c3a * y * (-3.0f * x2 + y2); o[10] = 2.8906114426405538f * xy * z; o[11] = c3b * y * (1.0f - 5.0f * z2);
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f); o[13] = c3b * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2); o[15] = c3a * x * (-x2 + 3.0f * y2);
+    if (degree <= 4) return;
+    const float x4 = x2 * x2, y4 = y2 * y2, z4 = z2 * z2;
+    const float c4a = 1.7701307697799304f, c4b = 0.66904654355728921f;
+    o[16] = 2.5033429417967046f * xy * (x2 - y2); o[17] = c4a * yz * (-3.0f * x2 + y2);
+    o[18] = 0.94617469575756008f * xy * (7.0f * z2 - 1.0f); o[19] = c4b * yz * (3.0f - 7.0f * z2);
+    o[20] = -3.1735664074561294f * z2 + 3.7024941420321507f * z4 + 0.31735664074561293f;
+    o[21] = c4b * xz * (3.0f - 7.0f * z2); o[22] = 0.47308734787878004f * (x2 - y2) * (7.0f * z2 - 1.0f);
+    o[23] = c4a * xz * (-x2 + 3.0f * y2);
+    o[24] = -3.7550144126950569f * x2 * y2 + 0.62583573544917614f * x4 + 0.62583573544917614f * y4;
+    if (degree <= 5) return;
+    const float c5a = 0.65638205684017015f, c5b = 0.48923829943525038f, c5c = 0.45294665119569694f;
+    o[25] = c5a * y * (10.0f * x2 * y2 - 5.0f * x4 - y4); o[26] = 8.3026492595241645f * xy * z * (x2 - y2);
+    o[27] = -c5b * y * (3.0f * x2 - y2) * (9.0f * z2 - 1.0f); o[28] = 4.7935367849733241f * xy * z * (3.0f * z2 - 1.0f);
+    o[29] = c5c * y * (14.0f * z2 - 21.0f * z4 - 1.0f); o[30] = 0.1169503224534236f * z * (-70.0f * z2 + 63.0f * z4 + 15.0f);
+    o[31] = c5c * x * (14.0f * z2 - 21.0f * z4 - 1.0f); o[32] = 2.3967683924866621f * z * (x2 - y2) * (3.0f * z2 - 1.0f);
+    o[33] = -c5b * x * (x2 - 3.0f * y2) * (9.0f * z2 - 1.0f); o[34] = 2.0756623148810411f * z * (-6.0f * x2 * y2 + x4 + y4);
+    o[35] = c5a * x * (10.0f * x2 * y2 - x4 - 5.0f * y4);
+    if (degree <= 6) return;
+    const float x6 = x4 * x2, y6 = y4 * y2, z6 = z4 * z2;
+    const float c6a = 2.3666191622317521f, c6b = 0.92120525951492349f, c6c = 0.58262136251873131f;
+    o[36] = 1.3663682103838286f * xy * (-10.0f * x2 * y2 + 3.0f * x4 + 3.0f * y4); o[37] = c6a * yz * (10.0f * x2 * y2 - 5.0f * x4 - y4);
+    o[38] = 2.0182596029148963f * xy * (x2 - y2) * (11.0f * z2 - 1.0f); o[39] = -c6b * yz * (3.0f * x2 - y2) * (11.0f * z2 - 3.0f);
+    o[40] = c6b * xy * (-18.0f * z2 + 33.0f * z4 + 1.0f); o[41] = c6c * yz * (30.0f * z2 - 33.0f * z4 - 5.0f);
+    o[42] = 6.6747662381009842f * z2 - 20.024298714302954f * z4 + 14.684485723822165f * z6 - 0.31784601133814211f;
+    o[43] = c6c * xz * (30.0f * z2 - 33.0f * z4 - 5.0f);
+    o[44] = 0.46060262975746175f * (x2 - y2) * (11.0f * z2 * (3.0f * z2 - 1.0f) - 7.0f * z2 + 1.0f);
+    o[45] = -c6b * xz * (x2 - 3.0f * y2) * (11.0f * z2 - 3.0f); o[46] = 0.50456490072872406f * (11.0f * z2 - 1.0f) * (-6.0f * x2 * y2 + x4 + y4);
+    o[47] = c6a * xz * (10.0f * x2 * y2 - x4 - 5.0f * y4);
+    o[48] = 10.247761577878714f * x2 * y4 - 10.247761577878714f * x4 * y2 + 0.6831841051919143f * x6 - 0.6831841051919143f * y6;
+}
+template <int DEG>
+__global__ void __launch_bounds__(128) k_spherical_harmonics(int n, const float* __restrict__ dirs, float* __restrict__ out) {
+    constexpr int C = DEG * DEG;
+    __shared__ float tile[128 * C];
+    int i = blockIdx.x * 128 + threadIdx.x;
+    if (i < n) {
+        float v[C];
+        sh_eval(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], DEG, v);
+#pragma unroll
+        for (int c = 0; c < C; c++) tile[threadIdx.x * C + c] = v[c];
+    }
+    __syncthreads();
+    long long base = (long long)blockIdx.x * 128 * C;
+    int cnt = min(128, n - blockIdx.x * 128) * C;
+    for (int k = threadIdx.x; k < cnt; k += 128) out[base + k] = tile[k];
+}
+
+// PermutoSDFGPU.cuh:24-127
+__global__ void __launch_bounds__(kThreads)
+k_random_rays_from_reel(int nr_rays, int H, int W, const float* __restrict__ rgb_reel, const float* __restrict__ mask_reel,
+                        const float* __restrict__ K, const float* __restrict__ tf, const int* __restrict__ pix,
+                        const int* __restrict__ img, bool has_mask, float* __restrict__ o_out, float* __restrict__ d_out,
+                        float* __restrict__ gt_rgb, float* __restrict__ gt_mask) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nr_rays) return;
+    int im = img[i], p = pix[i];
+    float sx = (float)(p % W) + 0.5f, sy = (float)(p / W) + 0.5f;
+    const float* Ki = K + 9 * im;
+    const float* T = tf + 16 * im;
+    float cxp = (sx - Ki[2]) / Ki[0], cyp = (sy - Ki[5]) / Ki[4];
+    float tx = T[3], ty = T[7], tz = T[11];
+    float wx = T[0] * cxp + T[1] * cyp + T[2] + tx;
+    float wy = T[4] * cxp + T[5] * cyp + T[6] + ty;
+    float wz = T[8] * cxp + T[9] * cyp + T[10] + tz;
+    float vx = wx - tx, vy = wy - ty, vz = wz - tz;
+    float inv = rsqrtf(vx * vx + vy * vy + vz * vz);
+    int x = (int)floorf(sx), y = (int)floorf(sy);
+    float m = has_mask ? mask_reel[((size_t)im * H + y) * W + x] : 1.0f;
+    o_out[3 * i] = tx; o_out[3 * i + 1] = ty; o_out[3 * i + 2] = tz;
+    d_out[3 * i] = vx * inv; d_out[3 * i + 1] = vy * inv; d_out[3 * i + 2] = vz * inv;
+    size_t plane = (size_t)H * W;
+    size_t base = (size_t)im * 3 * plane + (size_t)y * W + x;
+    gt_rgb[3 * i] = rgb_reel[base] * m;
+    gt_rgb[3 * i + 1] = rgb_reel[base + plane] * m;
+    gt_rgb[3 * i + 2] = rgb_reel[base + 2 * plane] * m;
+    gt_mask[i] = m;
+}
+
+inline GridGeom geom(int V, float extent, const float* t) { GridGeom g; g.V = V; g.extent = extent; g.tx = t[0]; g.ty = t[1]; g.tz = t[2]; return g; }
+#define ST ((cudaStream_t)stream)
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+int psdf_sphere_ray_intersection(int nr_rays, float radius, const float center[3], const float* origins, const float* dirs,
+                                 float* pts_entry, float* t_entry, float* pts_exit, float* t_exit, uint8_t* hit, void* stream) {
+    if (nr_rays < 0) return PSDF_ERR_ARG;
+    if (nr_rays == 0) return PSDF_OK;
+    k_sphere_ray_intersection<<<div_up(nr_rays, kThreads), kThreads, 0, ST>>>(nr_rays, radius, center[0], center[1], center[2],
+                                                                             origins, dirs, pts_entry, t_entry, pts_exit,
+                                                                             t_exit, hit);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_sphere_rand_points_inside(int n, float radius, const float* phi, const float* costheta, const float* u, float* points,
+                                   void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_sphere_rand_points<<<div_up(n, kThreads), kThreads, 0, ST>>>(n, radius, phi, costheta, u, points);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_sphere_check_point_inside(int n, float radius, const float center[3], const float* points, uint8_t* out, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_sphere_inside<<<div_up(n, kThreads), kThreads, 0, ST>>>(n, radius, center[0], center[1], center[2], points, out);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+
+int psdf_occ_compute_grid_points(int n, int V, float extent, const float trans[3], const int* idx, uint64_t rng_state,
+                                 uint64_t rng_inc, int randomize, float* out, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_occ_grid_points<<<div_up(n, kThreads), kThreads, 0, ST>>>(n, geom(V, extent, trans), idx, Pcg32(rng_state, rng_inc),
+                                                               randomize != 0, out);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_occ_update_with_density(int n, const float* density, const int* idx, float decay, float thresh, float* values,
+                                 uint8_t* occ, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_occ_update_density<<<div_up(n, kThreads), kThreads, 0, ST>>>(n, density, idx, decay, thresh, values, occ);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_occ_update_with_sdf(int n, const float* sdf, const int* idx, float extent, int V, float inv_s, const float* inv_s_dev,
+                             float thresh, int random_sample_variant, float* values, uint8_t* occ, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    // error range of the sdf inside a voxel: 1.3 (full grid, :437) or 1.0 (random subset, :497) half diagonals
+    float voxel = extent / (float)V;
+    float half = (float)((double)voxel / 2.0);
+    float half_diag = sqrtf(3.0f) * half;
+    float range = random_sample_variant ? (float)(1.0 * (double)half_diag) : (float)(1.3 * (double)half_diag);
+    k_occ_update_sdf<<<div_up(n, kThreads), kThreads, 0, ST>>>(n, sdf, idx, range, inv_s, inv_s_dev, thresh, values, occ);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_occ_check_occupancy(int n, int V, float extent, const float trans[3], const uint8_t* occ, const float* points,
+                             uint8_t* out, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_occ_check<<<div_up(n, kThreads), kThreads, 0, ST>>>(n, geom(V, extent, trans), occ, points, out);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_occ_compute_samples_in_occupied_regions(int nr_rays, int V, float extent, const float trans[3], const float* origins,
+                                                 const float* dirs, const float* t_entry, const float* t_exit,
+                                                 const uint8_t* occ, float min_dist, int max_per_ray, int max_nr_samples,
+                                                 uint64_t rng_state, uint64_t rng_inc, int jitter, int slot_mode,
+                                                 float* s_pos, float* s_dirs, float* s_z, float* s_dt, float* ray_fixed_dt,
+                                                 int* ray_start_end, int* cur_nr_samples, void* stream) {
+    if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    if (slot_mode == 1 && (long long)nr_rays * max_per_ray > (long long)max_nr_samples) return PSDF_ERR_ARG;
+    // 128-thread blocks: 512 rays spread over 4 SMs instead of 2; the kernel is latency bound, not occupancy bound
+    k_occ_samples_in_occupied<<<div_up(nr_rays, 64), 64, 0, ST>>>(nr_rays, geom(V, extent, trans), origins, dirs, t_entry, t_exit,
+                                                                 occ, min_dist, max_per_ray, max_nr_samples,
+                                                                 Pcg32(rng_state, rng_inc), jitter != 0, slot_mode, s_pos,
+                                                                 s_dirs, s_z, s_dt, ray_fixed_dt, ray_start_end,
+                                                                 cur_nr_samples);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_occ_compute_first_sample_start(int nr_rays, int V, float extent, const float trans[3], const float* origins,
+                                        const float* dirs, const float* t_entry, const float* t_exit, const uint8_t* occ,
+                                        int max_nr_samples, int slot_mode, float* s_pos, float* s_dirs, float* s_z, float* s_dt,
+                                        float* ray_fixed_dt, int* ray_start_end, int* cur_nr_samples, void* stream) {
+    if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    if (slot_mode == 1 && nr_rays > max_nr_samples) return PSDF_ERR_ARG;
+    k_occ_first_sample<<<div_up(nr_rays, 128), 128, 0, ST>>>(nr_rays, geom(V, extent, trans), origins, dirs, t_entry, t_exit, occ,
+                                                            max_nr_samples, slot_mode, s_pos, s_dirs, s_z, s_dt, ray_fixed_dt,
+                                                            ray_start_end, cur_nr_samples);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_occ_advance_sample_to_next_occupied_voxel(int n, int V, float extent, const float trans[3], const float* dirs,
+                                                   float* pos_io, const uint8_t* occ, uint8_t* within, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_occ_advance_to_next_occupied<<<div_up(n, 128), 128, 0, ST>>>(n, geom(V, extent, trans), dirs, pos_io, occ, within);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+
+int psdf_sampler_fg(int nr_rays, const float* origins, const float* dirs, const float* t_entry, const float* t_exit,
+                    float min_dist, int max_per_ray, int max_nr_samples, uint64_t rng_state, uint64_t rng_inc, int jitter,
+                    int slot_mode, float* s_pos, float* s_dirs, float* s_z, float* s_dt, float* ray_fixed_dt,
+                    int* ray_start_end, int* cur_nr_samples, void* stream) {
+    if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    if (slot_mode == 1 && (long long)nr_rays * max_per_ray > (long long)max_nr_samples) return PSDF_ERR_ARG;
+    k_sampler_fg<<<div_up(nr_rays, 64), 64, 0, ST>>>(nr_rays, origins, dirs, t_entry, t_exit, min_dist, max_per_ray,
+                                                    max_nr_samples, Pcg32(rng_state, rng_inc), jitter != 0, slot_mode, s_pos,
+                                                    s_dirs, s_z, s_dt, ray_fixed_dt, ray_start_end, cur_nr_samples);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_sampler_bg(int nr_rays, int n_per_ray, const float* origins, const float* dirs, const float* t_exit,
+                    float sphere_radius, const float sphere_center[3], uint64_t rng_state, uint64_t rng_inc, int randomize,
+                    int contract, float* s3, float* s4, float* s_dirs, float* s_z, float* s_dt, float* ray_fixed_dt,
+                    int* ray_start_end, void* stream) {
+    if (nr_rays <= 0 || n_per_ray < 2) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_sampler_bg<<<div_up(nr_rays, 64), 64, 0, ST>>>(nr_rays, n_per_ray, origins, dirs, t_exit, sphere_radius, sphere_center[0],
+                                                    sphere_center[1], sphere_center[2], Pcg32(rng_state, rng_inc),
+                                                    randomize != 0, contract != 0, s3, s4, s_dirs, s_z, s_dt, ray_fixed_dt,
+                                                    ray_start_end);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+
+long long psdf_packed_compact_workspace_bytes(int nr_rays) {
+    int nblocks = div_up(nr_rays > 0 ? nr_rays : 1, kScanThreads);
+    return (long long)sizeof(int) * ((long long)nr_rays + nblocks + 1);
+}
+int psdf_packed_count_samples(int nr_rays, const int* ray_start_end, int* total_dev, void* stream) {
+    cudaMemsetAsync(total_dev, 0, sizeof(int), ST);
+    if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    int blocks = min(div_up(nr_rays, kScanThreads), 148);
+    k_count_samples<<<blocks, kScanThreads, 0, ST>>>(nr_rays, ray_start_end, total_dev);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+// workspace layout: [offsets: nr_rays][block_sums: nblocks][total: 1]; total is also the device count after the call
+int psdf_packed_compact_scan(int nr_rays, const int* ray_start_end, int* workspace, void* stream) {
+    if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    int nblocks = div_up(nr_rays, kScanThreads);
+    int* offsets = workspace;
+    int* block_sums = workspace + nr_rays;
+    int* total = block_sums + nblocks;
+    k_scan_counts_local<<<nblocks, kScanThreads, 0, ST>>>(nr_rays, ray_start_end, offsets, block_sums);
+    k_scan_block_sums<<<1, kScanThreads, 0, ST>>>(nblocks, block_sums, total);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_packed_compact_copy(int nr_rays, const float* pos, const float* pos4, const float* dirs, const float* z,
+                             const float* dt, const float* sdf, const float* fixed_dt, const int* ray_start_end,
+                             const int* workspace, float* o_pos, float* o_pos4, float* o_dirs, float* o_z, float* o_dt,
+                             float* o_sdf, float* o_fixed_dt, int* o_start_end, void* stream) {
+    if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    const int* offsets = workspace;
+    const int* block_sums = workspace + nr_rays;
+    k_compact_copy<<<div_up((long long)nr_rays * 32, kThreads), kThreads, 0, ST>>>(nr_rays, pos, pos4, dirs, z, dt, sdf, fixed_dt,
+                                                                                  ray_start_end, offsets, block_sums, o_pos,
+                                                                                  o_pos4, o_dirs, o_z, o_dt, o_sdf, o_fixed_dt,
+                                                                                  o_start_end);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_packed_per_sample_ray_idx(int nr_rays, int nr_samples, const int* ray_start_end, int* out, void* stream) {
+    if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_per_sample_ray_idx<<<div_up((long long)nr_rays * 32, kThreads), kThreads, 0, ST>>>(nr_rays, nr_samples, ray_start_end, out);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+
+int psdf_spherical_harmonics(int n, int degree, const float* dirs, float* out, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    int blocks = div_up(n, 128);
+    switch (degree) {
+        case 1: k_spherical_harmonics<1><<<blocks, 128, 0, ST>>>(n, dirs, out); break;
+        case 2: k_spherical_harmonics<2><<<blocks, 128, 0, ST>>>(n, dirs, out); break;
+        case 3: k_spherical_harmonics<3><<<blocks, 128, 0, ST>>>(n, dirs, out); break;
+        case 4: k_spherical_harmonics<4><<<blocks, 128, 0, ST>>>(n, dirs, out); break;
+        case 5: k_spherical_harmonics<5><<<blocks, 128, 0, ST>>>(n, dirs, out); break;
+        case 6: k_spherical_harmonics<6><<<blocks, 128, 0, ST>>>(n, dirs, out); break;
+        case 7: k_spherical_harmonics<7><<<blocks, 128, 0, ST>>>(n, dirs, out); break;
+        default: return PSDF_ERR_ARG;
+    }
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_random_rays_from_reel(int nr_rays, int nr_images, int H, int W, const float* rgb_reel, const float* mask_reel,
+                               const float* K, const float* tf_world_cam, const int* pixel_indices, const int* img_indices,
+                               int has_mask, float* origins, float* dirs, float* gt_rgb, float* gt_mask, void* stream) {
+    (void)nr_images;
+    if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_random_rays_from_reel<<<div_up(nr_rays, kThreads), kThreads, 0, ST>>>(nr_rays, H, W, rgb_reel, mask_reel, K, tf_world_cam,
+                                                                           pixel_indices, img_indices, has_mask != 0, origins,
+                                                                           dirs, gt_rgb, gt_mask);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+
+}  // extern "C"
