@@ -416,11 +416,11 @@ k_sampler_bg(int nr_rays, int n_per_ray, const float* __restrict__ origins, cons
     float t_between = (float)((1.0 - (double)min_t) / (double)(n_per_ray - 1));
     float prev_z = 0;
     for (int i = 0; i < n_per_ray; i++) {
-        float t_sample = (float)(1.0 - (double)__fmul_rn((float)i, t_between));
+        float t_sample = __fmaf_rn(-t_between, (float)i, 1.0f);   // contracted to one FFMA in the reference SASS
         if (randomize) {
             rng.advance((int64_t)(idx * n_per_ray));
             float rnd = rng.next_float();
-            float mov = (float)((double)__fmul_rn(t_between, rnd) - (double)t_between / 2.0);
+            float mov = __fmaf_rn(t_between, rnd, -__fmul_rn(t_between, 0.5f));
             t_sample = __fadd_rn(t_sample, mov);
         }
         t_sample = clampf(t_sample, min_t, 1.0f);

@@ -129,7 +129,8 @@ k_integrate(int nr_rays, int max_nr_samples, const int* __restrict__ start_end, 
 
 __device__ __forceinline__ float map_range(float v, float is, float ie, float os, float oe) {
     float c = fmaxf(is, fminf(ie, v));
-    return __fadd_rn(os, __fmul_rn(__fdiv_rn(__fsub_rn(oe, os), __fsub_rn(ie, is)), __fsub_rn(c, is)));
+    // os + ratio*(c-is): one FFMA in the reference build
+    return __fmaf_rn(__fsub_rn(c, is), __fdiv_rn(__fsub_rn(oe, os), __fsub_rn(ie, is)), os);
 }
 __device__ __forceinline__ float sigmoid_ref(float x) { return (float)(1.0 / (1.0 + (double)expf(-x))); }
 
@@ -369,7 +370,7 @@ k_integrate_backward(int nr_rays, int max_nr_samples, const int* __restrict__ st
         float c0 = vals[3 * s], c1 = vals[3 * s + 1], c2 = reference_bug ? c1 : vals[3 * s + 2];
         float ws = w[s];
         g_vals[3 * s] = __fmul_rn(gx, ws); g_vals[3 * s + 1] = __fmul_rn(gy, ws); g_vals[3 * s + 2] = __fmul_rn(gz, ws);
-        g_w[s] = __fmaf_rn(gz, c2, __fmaf_rn(gy, c1, __fmul_rn(gx, c0)));
+        g_w[s] = __fmaf_rn(gz, c2, __fmaf_rn(gx, c0, __fmul_rn(gy, c1)));   // reference SASS order
     }
 }
 // VolumeRenderingGPU.cuh:1271-1329

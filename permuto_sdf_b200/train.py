@@ -1,0 +1,299 @@
+"""Hot-path drivers: sample creation, SDF importance resampling, the rendering forward (`run_net`), the
+losses and one training iteration, and the sphere tracer.
+
+Mirror of the orchestration in the reference (same function names and argument meaning):
+  create_samples                   permuto_sdf_py/utils/nerf_utils.py:502-526
+  importance_sampling_sdf_model    permuto_sdf_py/utils/sdf_utils.py:383-423
+  sphere_trace                     permuto_sdf_py/utils/sdf_utils.py:120-218
+  run_net / run_net_sphere_traced  permuto_sdf_py/train_permuto_sdf.py:111-170,211-242
+  rgb_loss / eikonal_loss / ...    permuto_sdf_py/utils/permuto_sdf_utils.py:43-88
+  train iteration                  permuto_sdf_py/train_permuto_sdf.py:311-422
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from .models import RGB, SDF, Colorcal, NerfHash, map_range_val
+from .permuto_sdf import OccupancyGrid, PermutoSDF, RaySampler, RaySamplesPacked, Sphere, VolumeRendering
+
+
+class HyperParams:
+    """train_permuto_sdf.py:77-105 (defaults of the reference); the synthetic bench overrides sizes"""
+    s_mult = 1.0
+    lr = 1e-3
+    nr_iter_sphere_fit = 4000
+    forced_variance_finish_iter = 35000
+    eikonal_weight = 0.04
+    curvature_weight = 0.65
+    lipshitz_weight = 3e-6
+    mask_weight = 0.1
+    offsurface_weight = 1e-4
+    iter_start_reduce_curv = 50000
+    iter_finish_reduce_curv = 50000 + 1001
+    forced_variance_finish = 0.8
+    use_occupancy_grid = True
+    nr_samples_bg = 32
+    min_dist_between_samples = 0.0001
+    max_nr_samples_per_ray = 64
+    nr_samples_imp_sampling = 16
+    do_importance_sampling = True
+    use_color_calibration = True
+    nr_rays = 512
+    sdf_geom_feat_size = 32
+    sdf_nr_iters_for_c2f = 10000
+    rgb_nr_iters_for_c2f = 1
+    background_nr_iters_for_c2f = 1
+    target_nr_of_samples = 512 * (64 + 16 + 16)
+    with_mask = True
+
+
+def create_samples(with_mask, hyperparams, ray_origins, ray_dirs, jitter_samples, occupancy_grid, bounding_primitive):
+    _, ray_t_entry, _, ray_t_exit, _ = bounding_primitive.ray_intersection(ray_origins, ray_dirs)
+    if hyperparams.use_occupancy_grid and occupancy_grid is not None:
+        fg = occupancy_grid.compute_samples_in_occupied_regions(ray_origins, ray_dirs, ray_t_entry, ray_t_exit,
+                                                                hyperparams.min_dist_between_samples,
+                                                                hyperparams.max_nr_samples_per_ray, jitter_samples)
+    else:
+        fg = RaySampler.compute_samples_fg(ray_origins, ray_dirs, ray_t_entry, ray_t_exit, hyperparams.min_dist_between_samples,
+                                           hyperparams.max_nr_samples_per_ray, bounding_primitive.m_radius,
+                                           bounding_primitive.m_center_tensor, jitter_samples)
+    fg = fg.compact_to_valid_samples()
+    bg = None
+    if not with_mask:
+        bg = RaySampler.compute_samples_bg(ray_origins, ray_dirs, ray_t_exit, hyperparams.nr_samples_bg, bounding_primitive.m_radius,
+                                           bounding_primitive.m_center_tensor, jitter_samples, False)
+    return fg, bg
+
+
+def _imp_round(rsp, sdf, inv_s, inv_s_multiplier, ray_origins, ray_dirs, nr_imp, jitter):
+    alpha = VolumeRendering.sdf2alpha(rsp, sdf, inv_s, True, inv_s_multiplier).clip(0.0, 1.0)
+    T, _ = VolumeRendering.cumprod_alpha2transmittance(rsp, 1 - alpha + 1e-7)
+    weights = alpha * T
+    _, wsum_per_sample = VolumeRendering.sum_over_each_ray(rsp, weights)
+    weights = weights / torch.clamp(wsum_per_sample, min=1e-6)
+    cdf = VolumeRendering.compute_cdf(rsp, weights)
+    return VolumeRendering.importance_sample(ray_origins, ray_dirs, rsp, cdf, nr_imp, jitter)
+
+
+def importance_sampling_sdf_model(model_sdf, rsp, ray_origins, ray_dirs, ray_t_exit, iter_nr_for_anneal, nr_imp=16):
+    inv_s_imp_sampling = 512
+    sdf, _ = model_sdf(rsp.samples_pos, iter_nr_for_anneal)
+    rsp.set_sdf(sdf)
+    imp = _imp_round(rsp, sdf, inv_s_imp_sampling, 1.0, ray_origins, ray_dirs, nr_imp, model_sdf.training)
+    sdf_imp, _ = model_sdf(imp.samples_pos, iter_nr_for_anneal)
+    imp.set_sdf(sdf_imp)
+    rsp = VolumeRendering.combine_uniform_samples_with_imp(ray_origins, ray_dirs, ray_t_exit, rsp, imp).compact_to_valid_samples()
+    # second round: sharper density, reuse the merged sdf (no network evaluation)
+    imp = _imp_round(rsp, rsp.samples_sdf, inv_s_imp_sampling, 2.0, ray_origins, ray_dirs, nr_imp, model_sdf.training)
+    rsp.remove_sdf()
+    rsp = VolumeRendering.combine_uniform_samples_with_imp(ray_origins, ray_dirs, ray_t_exit, rsp, imp).compact_to_valid_samples()
+    return rsp
+
+
+def run_net(with_mask, hyperparams, ray_origins, ray_dirs, img_indices, model_sdf, model_rgb, model_bg, model_colorcal, occupancy_grid,
+            iter_nr_for_anneal, cos_anneal_ratio, forced_variance):
+    with torch.no_grad():
+        _, _, _, ray_t_exit, _ = model_sdf.boundary_primitive.ray_intersection(ray_origins, ray_dirs)
+        fg, bg = create_samples(with_mask, hyperparams, ray_origins, ray_dirs, model_sdf.training, occupancy_grid,
+                                model_sdf.boundary_primitive)
+        if hyperparams.do_importance_sampling and fg.samples_pos.shape[0] != 0:
+            fg = importance_sampling_sdf_model(model_sdf, fg, ray_origins, ray_dirs, ray_t_exit, iter_nr_for_anneal,
+                                               hyperparams.nr_samples_imp_sampling)
+    if fg.samples_pos.shape[0] == 0:
+        pred_rgb = torch.zeros_like(ray_origins)
+        pred_normals = torch.zeros_like(ray_origins)
+        sdf_gradients = torch.zeros_like(ray_origins)
+        weights_sum = torch.zeros_like(ray_origins)[:, 0:1]
+        bg_transmittance = torch.ones_like(ray_origins)[:, 0:1]
+    else:
+        sdf, sdf_gradients, geom_feat = model_sdf.get_sdf_and_gradient(fg.samples_pos, iter_nr_for_anneal)
+        rgb_samples = model_rgb(fg.samples_pos, fg.samples_dirs, sdf_gradients, geom_feat, iter_nr_for_anneal, model_colorcal, img_indices,
+                                fg.ray_start_end_idx)
+        weights, weights_sum, bg_transmittance, inv_s = model_rgb.volume_renderer_neus.compute_weights(fg, sdf, sdf_gradients,
+                                                                                                       cos_anneal_ratio, forced_variance)
+        pred_rgb = model_rgb.volume_renderer_neus.integrate(fg, rgb_samples, weights)
+        pred_normals = F.normalize(model_rgb.volume_renderer_neus.integrate(fg, sdf_gradients, weights), dim=1)
+    pred_rgb_bg = None
+    if not with_mask and bg is not None and bg.samples_pos_4d.shape[0] != 0:
+        rgb_bg, density_bg = model_bg(bg.samples_pos_4d, bg.samples_dirs, iter_nr_for_anneal, model_colorcal, img_indices,
+                                      ray_start_end_idx=bg.ray_start_end_idx)
+        weights_bg, _, _ = model_bg.volume_renderer_nerf.compute_weights(bg, density_bg.view(-1, 1))
+        pred_rgb_bg = bg_transmittance.view(-1, 1) * model_bg.volume_renderer_nerf.integrate(bg, rgb_bg, weights_bg)
+        pred_rgb = pred_rgb + pred_rgb_bg
+    return pred_rgb, pred_rgb_bg, pred_normals, sdf_gradients, weights_sum, fg
+
+
+def rgb_loss(gt_rgb, pred_rgb, does_ray_intersect_primitive):
+    return ((gt_rgb - pred_rgb).abs() * does_ray_intersect_primitive * 1.0).mean()
+
+
+def eikonal_loss(sdf_gradients):
+    return ((torch.linalg.norm(sdf_gradients.reshape(-1, 3), ord=2, dim=-1) - 1.0) ** 2).mean()
+
+
+def sdf_loss_sphere(points, sdf, sdf_gradients, sphere_radius, sphere_center, distance_scale=1.0):
+    """permuto_sdf_utils.py sphere-init loss: |sdf - (||x-c|| - r)| + eikonal"""
+    c = torch.as_tensor(sphere_center, dtype=points.dtype, device=points.device).view(1, 3)
+    gt = ((points - c).norm(dim=-1, keepdim=True) - sphere_radius) * distance_scale
+    loss_sdf = ((sdf - gt) ** 2).mean()
+    loss_eik = ((sdf_gradients.norm(dim=-1) - distance_scale) ** 2).mean()
+    return loss_sdf * 3e3 + loss_eik * 5e1, loss_sdf, loss_eik
+
+
+def loss_sphere_init(nr_points, aabb, model, iter_nr_for_anneal):
+    pts = aabb.rand_points_inside(nr_points=nr_points)
+    sdf, grads, _ = model.get_sdf_and_gradient(pts, iter_nr_for_anneal)
+    return sdf_loss_sphere(pts, sdf, grads, sphere_radius=0.3, sphere_center=[0, 0, 0])
+
+
+def sphere_trace(nr_sphere_traces, ray_origins, ray_dirs, model, return_gradients, sdf_multiplier, sdf_converged_tresh,
+                 occupancy_grid=None):
+    """sdf_utils.py:120-218 (boolean-mask gather/scatter loop, as in the reference)"""
+    ray_points_entry, ray_t_entry, _, ray_t_exit, _ = model.boundary_primitive.ray_intersection(ray_origins, ray_dirs)
+    has_occupancy = occupancy_grid is not None
+    if has_occupancy:
+        rsp = occupancy_grid.compute_first_sample_start_of_occupied_regions(ray_origins, ray_dirs, ray_t_entry, ray_t_exit)
+        rsp = rsp.compact_to_valid_samples()
+        pos, dirs = rsp.samples_pos, rsp.samples_dirs
+        pos = pos + dirs * (1.0 / occupancy_grid.get_nr_voxels_per_dim()) * 0.5
+    else:
+        rsp = RaySamplesPacked(ray_origins.shape[0], ray_origins.shape[0])
+        rsp.initialize_with_one_sample_per_ray(ray_points_entry, ray_dirs)
+        pos, dirs = rsp.samples_pos, rsp.samples_dirs
+    pts = pos.clone()
+    converged = torch.zeros_like(pos)[:, 0:1].bool()
+    for _ in range(nr_sphere_traces):
+        sel = torch.logical_not(converged).view(-1)
+        pos_u, dirs_u = pts[sel].contiguous(), dirs[sel].contiguous()
+        if pos_u.shape[0] == 0:
+            break
+        sdf, _ = model(pos_u, model.last_iter_nr)
+        pos_u = (pos_u + dirs_u * sdf * sdf_multiplier).contiguous()
+        newly = (sdf.abs() < sdf_converged_tresh).view(-1)
+        if has_occupancy:
+            pos_u, within = occupancy_grid.advance_sample_to_next_occupied_voxel(dirs_u, pos_u)
+        else:
+            within = model.boundary_primitive.check_point_inside_primitive(pos_u)
+        conv_u = torch.logical_or(newly, torch.logical_not(within.view(-1)))
+        converged[sel] = torch.logical_or(converged[sel].view(-1), conv_u).view(-1, 1)
+        pts[sel] = pos_u
+    if return_gradients:
+        with torch.enable_grad():
+            sdf, grads, geom = model.get_sdf_and_gradient(pts.detach().clone(), model.last_iter_nr)
+            grads = grads.detach()[:, 0:3]
+    else:
+        sdf, geom = model(pts, model.last_iter_nr)
+        grads = None
+    rsp.samples_pos = pts
+    return pts, sdf, grads, geom, rsp
+
+
+def run_net_sphere_traced(ray_origins, ray_dirs, hyperparams, model_sdf, model_rgb, occupancy_grid, iter_nr_for_anneal, nr_sphere_traces,
+                          sdf_multiplier, sdf_converged_tresh):
+    """train_permuto_sdf.py:211-242 without the frame->rays and image reshapes"""
+    ray_end, _, ray_end_gradient, geom_feat_end, traced = sphere_trace(nr_sphere_traces, ray_origins, ray_dirs, model_sdf, True,
+                                                                      sdf_multiplier, sdf_converged_tresh, occupancy_grid)
+    within = model_sdf.boundary_primitive.check_point_inside_primitive(ray_end).view(-1)
+    if hyperparams.use_occupancy_grid and occupancy_grid is not None:
+        within = torch.logical_and(occupancy_grid.check_occupancy(ray_end).view(-1), within)
+    weights = within.float().view(-1, 1).contiguous()
+    vr = model_rgb.volume_renderer_neus
+    pred_normals = F.normalize(vr.integrate(traced, ray_end_gradient.contiguous(), weights), dim=1)
+    rgb_samples = model_rgb(traced.samples_pos, traced.samples_dirs, ray_end_gradient, geom_feat_end, iter_nr_for_anneal)
+    pred_rgb = vr.integrate(traced, rgb_samples.contiguous(), weights)
+    pred_weights_sum, _ = VolumeRendering.sum_over_each_ray(traced, weights)
+    return pred_rgb, pred_normals, pred_weights_sum
+
+
+class Trainer:
+    """State of one PermutoSDF training run on synthetic data (models, occupancy grid, optimizer) and the
+    per-iteration step of train_permuto_sdf.py:311-422 (after sphere init), with `--with_mask` semantics."""
+
+    def __init__(self, hyperparams=None, nr_levels=24, capacity=2 ** 18, sdf_hidden=32, nr_images=8, occupancy_resolution=256,
+                 seed=0, with_colorcal=True, optimizer="adamw"):
+        torch.manual_seed(seed)
+        self.hp = hyperparams or HyperParams()
+        self.aabb = Sphere(0.5, [0, 0, 0])
+        hp = self.hp
+        self.model_sdf = SDF(3, self.aabb, hp.sdf_geom_feat_size, hp.sdf_nr_iters_for_c2f, nr_levels, capacity, sdf_hidden).to("cuda")
+        self.model_rgb = RGB(3, self.aabb, hp.sdf_geom_feat_size, hp.rgb_nr_iters_for_c2f, nr_levels, capacity).to("cuda")
+        self.model_bg = None if hp.with_mask else NerfHash(4, self.aabb, hp.background_nr_iters_for_c2f, nr_levels, capacity).to("cuda")
+        self.model_colorcal = Colorcal(nr_images, 0) if (hp.use_color_calibration and with_colorcal) else None
+        self.occupancy_grid = OccupancyGrid(occupancy_resolution, 1.0, [0, 0, 0]) if hp.use_occupancy_grid else None
+        groups = [{"params": list(self.model_sdf.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_sdf"}]
+        if self.model_bg is not None:
+            groups.append({"params": list(self.model_bg.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_bg"})
+        groups.append({"params": self.model_rgb.parameters_only_encoding(), "weight_decay": 0.0, "lr": hp.lr, "name": "model_rgb_only_encoding"})
+        groups.append({"params": self.model_rgb.parameters_all_without_encoding(), "weight_decay": 0.0, "lr": hp.lr,
+                       "name": "model_rgb_all_without_encoding"})
+        if self.model_colorcal is not None:
+            groups.append({"params": list(self.model_colorcal.parameters()), "weight_decay": 1e-1, "lr": hp.lr, "name": "model_colorcal"})
+        self.params = [p for g in groups for p in g["params"]]
+        self.optimizer = torch.optim.AdamW(groups, amsgrad=False, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, lr=hp.lr)
+        self.iter_nr = 0
+        self.nr_rays_to_create = hp.nr_rays
+        self.last = {}
+
+    def set_analytic_scene(self, object_radius=0.3, inv_s=512.0):
+        """occupancy of the analytic sphere SDF ||x|| - r through update_with_sdf"""
+        g = self.occupancy_grid
+        pts = g.compute_grid_points(False)
+        sdf = (pts.norm(dim=1, keepdim=True) - object_radius).contiguous()
+        g.update_with_sdf(sdf, inv_s, 1e10, 1e-4)
+
+    def losses(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal):
+        hp = self.hp
+        cos_anneal_ratio = map_range_val(iter_nr_for_anneal, 0.0, hp.forced_variance_finish_iter, 0.0, 1.0)
+        forced_variance = map_range_val(iter_nr_for_anneal, 0.0, hp.forced_variance_finish_iter, 0.3, hp.forced_variance_finish)
+        with torch.no_grad():
+            _, _, _, _, does_hit = self.aabb.ray_intersection(ray_origins, ray_dirs)
+        pred_rgb, _, _, sdf_gradients, weights_sum, fg = run_net(hp.with_mask, hp, ray_origins, ray_dirs, img_indices, self.model_sdf,
+                                                                 self.model_rgb, self.model_bg, self.model_colorcal, self.occupancy_grid,
+                                                                 iter_nr_for_anneal, cos_anneal_ratio, forced_variance)
+        loss_rgb = rgb_loss(gt_rgb, pred_rgb, does_hit)
+        loss = loss_rgb
+        loss_eik = eikonal_loss(sdf_gradients)
+        loss = loss + loss_eik * hp.eikonal_weight
+        gw_curv = map_range_val(iter_nr_for_anneal, hp.iter_start_reduce_curv, hp.iter_finish_reduce_curv, 1.0, 0.0)
+        loss_curv = torch.zeros((), device=loss.device)
+        if gw_curv > 0.0 and fg.samples_pos.shape[0] != 0:
+            _, curv = self.model_sdf.get_sdf_and_curvature_1d_precomputed_gradient_normal_based(fg.samples_pos, sdf_gradients,
+                                                                                                iter_nr_for_anneal)
+            loss_curv = curv.mean()
+            loss = loss + loss_curv * hp.curvature_weight * gw_curv
+        if hp.use_occupancy_grid:
+            off = self.aabb.rand_points_inside(nr_points=1024)
+            sdf_rand, _ = self.model_sdf(off, iter_nr_for_anneal)
+            loss = loss + torch.exp(-1e2 * torch.abs(sdf_rand)).mean() * hp.offsurface_weight
+        loss_lip = self.model_rgb.mlp.lipshitz_bound_full()
+        if iter_nr_for_anneal >= hp.iter_start_reduce_curv:
+            loss = loss + loss_lip.mean() * hp.lipshitz_weight
+        if hp.with_mask:
+            loss = loss + F.binary_cross_entropy(weights_sum.clip(1e-3, 1.0 - 1e-3), gt_mask) * hp.mask_weight
+        self.last = dict(loss_rgb=loss_rgb.detach(), loss_eikonal=loss_eik.detach(), loss_curvature=loss_curv.detach(),
+                         nr_samples=fg.samples_pos.shape[0], fg=fg)
+        return loss
+
+    def update_occupancy(self, iter_nr_for_anneal):
+        """train_permuto_sdf.py:386-391 (every 8th iteration)"""
+        with torch.no_grad():
+            pts, idx = self.occupancy_grid.compute_random_sample_of_grid_points(256 * 256 * 4, True)
+            sdf_grid, _ = self.model_sdf(pts, iter_nr_for_anneal)
+            self.occupancy_grid.update_with_sdf_random_sample(idx, sdf_grid.contiguous(), self.model_rgb.volume_renderer_neus.get_last_inv_s(), 1e-4)
+
+    def step(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy=None, optimizer_step=True):
+        """forward + losses + backward (+ optimizer). Returns the detached loss tensor (no host sync)."""
+        self.model_sdf.train(); self.model_rgb.train()
+        it = self.iter_nr
+        loss = self.losses(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, it)
+        if update_occupancy is None:
+            update_occupancy = (it % 8 == 0)
+        if update_occupancy and self.hp.use_occupancy_grid:
+            self.update_occupancy(it)
+        self.optimizer.zero_grad(set_to_none=False)
+        loss.backward()
+        if optimizer_step:
+            self.optimizer.step()
+        self.iter_nr += 1
+        return loss.detach()

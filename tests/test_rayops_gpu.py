@@ -99,7 +99,7 @@ def test_grid_updates_and_lookup(scene):
     rng = np.random.RandomState(0)
     g = OccupancyGrid(V, 1.0, [0, 0, 0])
     pts = g.compute_grid_points(False)
-    sdf = (pts.norm(dim=1, keepdim=True) - scenes.OBJECT_RADIUS).contiguous()
+    sdf = T(scenes.analytic_sdf(N(pts)))          # same float32 sdf values as the oracle scene
     g.update_with_sdf(sdf, 512.0, 1e10, 1e-4)
     assert np.array_equal(N(g.get_grid_occupancy()).astype(np.uint8), scene["occ"]), "occupancy bits differ from oracle"
     assert np.array_equal(N(g.get_grid_values()), scene["values"])
