@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the PermutoSDF hot path on B200 (contract: see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA kernels through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the CPU (PyTorch-only) restatement of the
+                                                           reference's encoding+MLP step on the host cores
+
+Workload (BASELINE.json configs[1], "C2"): one training iteration of PermutoSDF (train_permuto_sdf.py:311-422,
+--with_mask) on synthetic data: 512 rays x (96 occupancy-grid samples + 2x16 importance samples) = 128 samples/ray
+(65 536 samples when every ray hits), 16-level permutohedral lattice (2^18 x 2 per level), 3x64 SDF MLP,
+Lipschitz RGB MLP, 256^3 occupancy grid of the analytic sphere SDF |x|-0.3. A step = ray generation, sampling,
+importance resampling, forward, losses, backward through the double backward, dense AdamW.
+Metric: rays/s (whole job). `value`: inputs resident on the device. `e2e`: per step the ray indices come from pinned
+host memory and the loss is read back. Multi-GPU: rays sharded by rank (weak scaling), one NCCL all-reduce of the
+flat gradient buffer per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "compat")]
+
+NR_RAYS = 512
+SAMPLES_PER_RAY = 128
+WORKLOAD = "C2: 512 rays x 128 samples (96 grid + 2x16 importance), 16-level lattice 2^18x2, 3x64 SDF MLP, RGB Lipschitz MLP, 256^3 occupancy, analytic sphere SDF"
+METRIC = "rays/sec (train fwd+bwd+AdamW, 512 rays x 128 samples x 16 levels x 2 feat)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.stop, self.th = index, [], False, None
+
+    def _run(self):
+        while not self.stop:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.th.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+
+
+def analytic_reel(nimg, H, W, f, device):
+    """TensorReel-shaped synthetic data: cameras on a radius-1.2 sphere looking at a shaded sphere of radius 0.3"""
+    g = torch.Generator().manual_seed(123)
+    rgb = torch.zeros(nimg, 3, H, W)
+    mask = torch.zeros(nimg, 1, H, W)
+    K = torch.zeros(nimg, 3, 3)
+    tf = torch.zeros(nimg, 4, 4)
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32) + 0.5, torch.arange(W, dtype=torch.float32) + 0.5, indexing="ij")
+    for i in range(nimg):
+        c = torch.randn(3, generator=g); c = 1.2 * c / c.norm()
+        zaxis = -c / c.norm()
+        up = torch.tensor([0.0, 1.0, 0.0])
+        xaxis = torch.linalg.cross(up, zaxis); xaxis = xaxis / xaxis.norm()
+        yaxis = torch.linalg.cross(zaxis, xaxis)
+        R = torch.stack([xaxis, yaxis, zaxis], 1)
+        K[i] = torch.tensor([[f, 0, W / 2.0], [0, f, H / 2.0], [0, 0, 1.0]])
+        tf[i, :3, :3], tf[i, :3, 3], tf[i, 3, 3] = R, c, 1.0
+        dcam = torch.stack([(xs - W / 2.0) / f, (ys - H / 2.0) / f, torch.ones_like(xs)], -1)
+        d = dcam @ R.t()
+        d = d / d.norm(dim=-1, keepdim=True)
+        b = (d * c).sum(-1); disc = b * b - (c.dot(c) - 0.09)
+        hit = disc > 0
+        t = -b - torch.sqrt(disc.clamp(min=0))
+        n = torch.nn.functional.normalize(c + t[..., None] * d, dim=-1)
+        col = (0.5 + 0.5 * n).permute(2, 0, 1)
+        rgb[i] = col * hit[None]
+        mask[i, 0] = hit.float()
+
+    class Reel:
+        pass
+    r = Reel()
+    r.rgb_reel, r.mask_reel, r.K_reel, r.tf_world_cam_reel = rgb.to(device), mask.to(device), K.to(device), tf.to(device)
+    return r
+
+
+def central_pixels(n, H, W, box, gen):
+    """pixel indices inside the central box x box window (all those rays hit the object)"""
+    x = torch.randint(W // 2 - box // 2, W // 2 + box // 2, (n,), generator=gen)
+    y = torch.randint(H // 2 - box // 2, H // 2 + box // 2, (n,), generator=gen)
+    return (y * W + x).to(torch.int32)
+
+
+class FlatGrads:
+    """all parameter gradients as views into one flat buffer -> a single NCCL all-reduce per step"""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(n, device=self.params[0].device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def allreduce_mean(self, world):
+        import torch.distributed as dist
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+        self.flat.mul_(1.0 / world)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from permuto_sdf_b200 import _lib, load_library
+    from permuto_sdf_b200.permuto_sdf import PermutoSDF
+    from permuto_sdf_b200.train import HyperParams, Trainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = load_library()
+    assert lib.psdf_device_ok() == 1
+
+    hp = HyperParams()
+    hp.max_nr_samples_per_ray = SAMPLES_PER_RAY - 2 * 16
+    hp.nr_samples_imp_sampling = 16
+    hp.nr_rays = NR_RAYS
+    tr = Trainer(hp, nr_levels=16, capacity=2 ** 18, sdf_hidden=64, nr_images=8, occupancy_resolution=256, seed=0)
+    tr.set_analytic_scene()
+    tr.iter_nr = 20000          # past coarse-to-fine: all 16 levels active, cos-anneal half way
+    H, W, f = 600, 800, 1000.0
+    reel = analytic_reel(8, H, W, f, dev)
+    flat = FlatGrads(tr.params) if world > 1 else None
+
+    total = args.steps + args.warmup
+    gen = torch.Generator().manual_seed(1000 + rank)
+    pix_host = [central_pixels(NR_RAYS, H, W, 300, gen).pin_memory() for _ in range(total)]
+    img_host = [torch.randint(0, 8, (NR_RAYS,), generator=gen, dtype=torch.int32).pin_memory() for _ in range(total)]
+    pix_dev = [p.to(dev) for p in pix_host]
+    img_dev = [p.to(dev) for p in img_host]
+
+    def one_step(i, e2e):
+        if e2e:
+            pix = pix_host[i].to(dev, non_blocking=True)
+            img = img_host[i].to(dev, non_blocking=True)
+        else:
+            pix, img = pix_dev[i], img_dev[i]
+        with torch.no_grad():
+            o, d, gt, gm, img_idx = PermutoSDF.rays_from_reel_indices(reel, pix, img)
+        loss = tr.step(o, d, gt, gm, img_idx, update_occupancy=(i % 8 == 0), optimizer_step=(flat is None))
+        if flat is not None:
+            flat.allreduce_mean(world)
+            tr.optimizer.step()
+        if e2e:
+            return float(loss)          # device -> host read of the step's result
+        return loss
+
+    def timed(e2e, with_events):
+        for i in range(args.warmup):
+            one_step(i, e2e)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        _lib.stats_begin(with_events=with_events)
+        evs = []
+        nsamples = 0
+        with ClockSampler(local) as cs:
+            for i in range(args.warmup, total):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                one_step(i, e2e)
+                e.record()
+                evs.append((s, e))
+                nsamples += tr.last["nr_samples"]
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        calls, launches, times = _lib.stats_end()
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, times, cs.summary(), nsamples / args.steps
+
+    ms_dev, launches, ktimes, clocks, avg_samples = timed(e2e=False, with_events=True)
+    ms_e2e, _, _, clocks2, _ = timed(e2e=True, with_events=False)
+    rays_total = NR_RAYS * world * args.steps
+    value = rays_total / (ms_dev / 1e3)
+    e2e_value = rays_total / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel of OUR library inside the timed region (CUDA events on the launch stream)
+    hbm, peak_src = peaks()
+    L, C, Ns = 16, 36, avg_samples
+    alg_bytes = {   # algorithmic bytes per launch, SURVEY.md 8(d)
+        "psdf_enc_forward": lambda: Ns * (12 + L * 4 * 8 + C * 4),
+        "psdf_enc_backward": lambda: Ns * (12 + L * 8 + L * 4 * 8 + L * 4 * 8),
+        "psdf_enc_double_backward": lambda: Ns * (12 + 12 + L * 8 + L * 4 * 8 + L * 4 * 8 + C * 4),
+        "psdf_sdf_fused_forward": lambda: Ns * (12 + L * 4 * 8 + 4 + 12 + 128),
+    }
+    roof = None
+    if ktimes:
+        top = sorted(((v[1], k) for k, v in ktimes.items()), reverse=True)
+        name = next((k for _, k in top if k in alg_bytes), top[0][1])
+        n, tot_ms = ktimes[name]
+        per_launch_s = tot_ms / n / 1e3
+        ach = (alg_bytes[name]() / per_launch_s / 1e9) if name in alg_bytes else None
+        roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None,
+                "traffic": None, "launches": n, "avg_us": per_launch_s * 1e6, "peak_source": peak_src,
+                "share_of_step": tot_ms / ms_dev,
+                "top5_ms_per_step": {k: round(v / args.steps, 4) for v, k in top[:5]}}
+
+    out = None
+    if rank == 0:
+        cpu = cpu_baseline(sample_rays=8, steps=3, warmup=1)
+        out = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "ours",
+            "config": {"workload": WORKLOAD, "rays_per_gpu": NR_RAYS, "avg_samples_per_step": avg_samples, "parallelism": "dp%d" % world,
+                       "l2": "per-step working set (2 lattice tables + grads + Adam moments ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
+                       "timed_region": "sum of per-step CUDA-event intervals"},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": NR_RAYS * 4 * 2 * world,
+                    "d2h_bytes_per_step": 4 * world},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def cpu_baseline(sample_rays, steps, warmup, threads=None):
+    """the reference path restated on the CPU (PyTorch only), bounded sample of the same workload"""
+    from oracle.cpu_step import time_cpu_step
+    threads = threads or os.cpu_count() or 1
+    med, ts = time_cpu_step(sample_rays, SAMPLES_PER_RAY, steps, warmup, threads)
+    return {"value": sample_rays / med, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": "%d rays x %d samples per step, %d steps, median; SDF encoding + 3x64 MLP forward, d sdf/dx, eikonal + feature loss, backward "
+                      "(double backward); the reference has no CPU path, this is the oracle restatement" % (sample_rays, SAMPLES_PER_RAY, steps),
+            "seconds_per_step": med}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    sample_rays = 16
+    cpu = cpu_baseline(sample_rays, steps=args.steps, warmup=min(args.warmup, 2))
+    out = {"metric": METRIC, "value": cpu["value"], "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": cpu["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "impl": "reference",
+           "config": {"workload": WORKLOAD, "note": "CPU PyTorch-only restatement on the host cores; each step is a bounded sample of %d rays" % sample_rays},
+           "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

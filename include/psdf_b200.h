@@ -157,6 +157,25 @@ int psdf_enc_double_backward(int N, int D, int L, int F, int T, const float* pos
                              const float* shift, const float* window, int concat_points, float points_scaling,
                              const float* gg_pos, const float* grad_out, float* grad_lattice, float* grad_grad_out, void* stream);
 
+/* ---------------------------------------------------------------- fused encoding + SDF MLP (tcgen05)
+ * Replaces SDF.forward / SDF.get_sdf_and_gradient of permuto_sdf_py/models/models.py:176-259 for evaluations that
+ * need no parameter gradients: importance sampling (sdf_utils.py:388,401), occupancy refresh
+ * (train_permuto_sdf.py:388-391), sphere tracing (sdf_utils.py:166,199-204).
+ * MLP = Linear(in,h) GELU Linear(h,h) GELU Linear(h,h) GELU Linear(h,out), weights in torch.nn.Linear layout.
+ * psdf_sdf_mlp_pack converts them once per weight update into the tensor-core operand blob. */
+long long psdf_sdf_mlp_blob_bytes(int in_dim, int hidden, int out_dim);
+int psdf_sdf_mlp_pack(int in_dim, int hidden, int out_dim, const float* W0, const float* b0, const float* W1, const float* b1,
+                      const float* W2, const float* b2, const float* W3, const float* b3, uint8_t* blob, void* stream);
+/* pos [N,3] -> sdf [N], grad [N,3] (NULL: value only), geom [N,out_dim-1] (NULL: skip). D = 3, F = 2, L % 4 == 0,
+ * concat_points on (in_dim = 2L + 4). */
+int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
+                           const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, float* sdf,
+                           float* grad, float* geom, void* stream);
+/* self-test of the tensor-core path: D[128,N] = A[128,K] * B[N,K]^T (N,K <= 64) */
+int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream);
+/* debug: choose which shared-memory-descriptor offset field carries the K-direction stride (0 = LBO, default) */
+int psdf_debug_set_desc_swap(int swap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,7 +134,43 @@ def call(name, *args):
             conv.append(float(a))
         else:
             conv.append(int(a))
-    rc = getattr(lib, name)(*conv)
+    if _STATS is not None:
+        _STATS["calls"][name] = _STATS["calls"].get(name, 0) + 1
+        if _STATS["events"] is not None:
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            rc = getattr(lib, name)(*conv)
+            e.record()
+            _STATS["events"].setdefault(name, []).append((s, e))
+        else:
+            rc = getattr(lib, name)(*conv)
+    else:
+        rc = getattr(lib, name)(*conv)
     if ret == "int" and rc != 0 and name not in _NON_STATUS:
         raise RuntimeError("%s failed with code %d" % (name, rc))
     return rc
+
+
+# ---- instrumentation used by bench.py: count C-ABI calls / kernel launches and time them with CUDA events on the
+# launching stream. Kernel launches per entry point (the rest launch exactly one kernel):
+_KERNELS_PER_CALL = {"psdf_packed_compact_scan": 2, "psdf_vr_combine_uniform_samples_with_imp": 3}
+_STATS = None
+
+
+def stats_begin(with_events=False):
+    global _STATS
+    _STATS = {"calls": {}, "events": {} if with_events else None}
+
+
+def stats_end():
+    """-> (calls per entry point, kernel launches, {name: (n, total_ms)} if events were recorded)"""
+    global _STATS
+    st, _STATS = _STATS, None
+    launches = sum(n * _KERNELS_PER_CALL.get(k, 1) for k, n in st["calls"].items())
+    times = {}
+    if st["events"] is not None:
+        import torch
+        torch.cuda.synchronize()
+        for k, evs in st["events"].items():
+            times[k] = (len(evs), sum(s.elapsed_time(e) for s, e in evs))
+    return st["calls"], launches, times

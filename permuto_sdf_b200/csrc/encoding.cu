@@ -24,6 +24,7 @@ using namespace psdf;
 namespace {
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kEncThreads = 128;
+constexpr int kGroups = kEncThreads / 32;   // level groups (warps) per block; a block covers 32 samples
 constexpr int kMaxLevels = 32;
 
 struct EncParams {
@@ -193,21 +194,22 @@ template <int D>
 __global__ void __launch_bounds__(kEncThreads)
 k_enc_forward(EncParams p, const float* __restrict__ pos, const float2* __restrict__ lattice, const float* __restrict__ scale,
               const float* __restrict__ shift, const float* __restrict__ window, float* __restrict__ out) {
+    // block = 32 consecutive samples x 4 level groups: warp g handles levels g, g+4, ... of the same 32 samples
     extern __shared__ float smem_dyn[];
     __shared__ LevelConsts lc;
     load_level_consts<D>(lc, scale, shift, window, p.L);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int stride = p.C + 1;                      // +1 float: conflict-free column writes
-    float* tile = smem_dyn + warp * 32 * stride;
-    const int n = blockIdx.x * kEncThreads + threadIdx.x;
+    float* tile = smem_dyn;
+    const int n = blockIdx.x * 32 + lane;
     const bool valid = n < p.N;
     float x[D];
 #pragma unroll
     for (int i = 0; i < D; i++) x[i] = valid ? pos[(size_t)n * D + i] : 0.0f;
 
-#pragma unroll 2
-    for (int l = 0; l < p.L; l++) {
+#pragma unroll 4
+    for (int l = warp; l < p.L; l += kGroups) {
         float cf[D], elevated[D + 1];
 #pragma unroll
         for (int i = 0; i < D; i++) cf[i] = __fmul_rn(__fadd_rn(x[i], lc.shift[l * 4 + i]), lc.scale[l * 4 + i]);
@@ -229,7 +231,7 @@ k_enc_forward(EncParams p, const float* __restrict__ pos, const float2* __restri
         tile[lane * stride + 2 * l] = a0;
         tile[lane * stride + 2 * l + 1] = a1;
     }
-    if (p.concat) {
+    if (p.concat && warp == kGroups - 1) {
         const int base = 2 * p.L;
         for (int c = base; c < p.C; c++) {
             int d = c - base;
@@ -239,17 +241,15 @@ k_enc_forward(EncParams p, const float* __restrict__ pos, const float2* __restri
             tile[lane * stride + c] = val;
         }
     }
-    __syncwarp();
-    // contiguous [rows, C] block of this warp
-    const int row0 = blockIdx.x * kEncThreads + warp * 32;
+    __syncthreads();
+    // contiguous [rows, C] block of this CTA, written by all 128 threads
+    const int row0 = blockIdx.x * 32;
     const int rows = min(32, p.N - row0);
-    if (rows > 0) {
-        float* dst = out + (size_t)row0 * p.C;
-        const int total = rows * p.C;
-        for (int e = lane; e < total; e += 32) {
-            int r = e / p.C, c = e - r * p.C;
-            dst[e] = tile[r * stride + c];
-        }
+    float* dst = out + (size_t)row0 * p.C;
+    const int total = rows * p.C;
+    for (int e = threadIdx.x; e < total; e += kEncThreads) {
+        int r = e / p.C, c = e - r * p.C;
+        dst[e] = tile[r * stride + c];
     }
 }
 
@@ -261,26 +261,39 @@ __global__ void __launch_bounds__(kEncThreads)
 k_enc_backward(EncParams p, const float* __restrict__ pos, const float2* __restrict__ lattice, const float* __restrict__ scale,
                const float* __restrict__ shift, const float* __restrict__ window, const float* __restrict__ grad_out,
                float* __restrict__ grad_lattice, float* __restrict__ grad_pos) {
+    extern __shared__ float smem_dyn[];
     __shared__ LevelConsts lc;
+    __shared__ float red[kGroups][32][4];
     load_level_consts<D>(lc, scale, shift, window, p.L);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = p.C + 1;
+    float* gtile = smem_dyn;                         // staged [32, C] block of grad_out (coalesced read)
+    const int row0 = blockIdx.x * 32;
+    {
+        const int rows = min(32, p.N - row0);
+        const float* src = grad_out + (size_t)row0 * p.C;
+        for (int e = threadIdx.x; e < 32 * p.C; e += kEncThreads) {
+            int r = e / p.C, c = e - r * p.C;
+            gtile[r * stride + c] = (r < rows) ? src[e] : 0.0f;
+        }
+    }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * kEncThreads + threadIdx.x;
+    const int n = row0 + lane;
     const bool valid = n < p.N;
     float x[D], gp[D];
 #pragma unroll
     for (int i = 0; i < D; i++) { x[i] = valid ? pos[(size_t)n * D + i] : 0.0f; gp[i] = 0.0f; }
-    const float* g_row = grad_out + (size_t)(valid ? n : 0) * p.C;
+    const float* g_row = gtile + lane * stride;
 
-#pragma unroll 1
-    for (int l = 0; l < p.L; l++) {
+#pragma unroll 2
+    for (int l = warp; l < p.L; l += kGroups) {
         float cf[D], elevated[D + 1];
 #pragma unroll
         for (int i = 0; i < D; i++) cf[i] = __fmul_rn(__fadd_rn(x[i], lc.shift[l * 4 + i]), lc.scale[l * 4 + i]);
         elevate<D>(cf, elevated);
         Simplex<D> s;
         locate<D>(elevated, s);
-        float2 g = valid ? *reinterpret_cast<const float2*>(g_row + 2 * l) : make_float2(0.f, 0.f);
+        float2 g = make_float2(g_row[2 * l], g_row[2 * l + 1]);
         float w = lc.window[l];
         unsigned idx[D + 1];
 #pragma unroll
@@ -312,15 +325,21 @@ k_enc_backward(EncParams p, const float* __restrict__ pos, const float2* __restr
             }
         }
     }
-    if (POS && valid) {
-        if (p.concat) {
-            const int base = 2 * p.L;
+    if (POS) {
+        // sum the per-level-group partial position gradients of the 4 warps
 #pragma unroll
-            for (int i = 0; i < D; i++)
-                if (base + i < p.C) gp[i] = fmaf(g_row[base + i], p.points_scaling, gp[i]);
+        for (int i = 0; i < D; i++) red[warp][lane][i] = gp[i];
+        __syncthreads();
+        if (warp == 0 && valid) {
+#pragma unroll
+            for (int i = 0; i < D; i++) {
+                float acc = red[0][lane][i];
+#pragma unroll
+                for (int w2 = 1; w2 < kGroups; w2++) acc += red[w2][lane][i];
+                if (p.concat && 2 * p.L + i < p.C) acc = fmaf(g_row[2 * p.L + i], p.points_scaling, acc);
+                grad_pos[(size_t)n * D + i] = acc;
+            }
         }
-#pragma unroll
-        for (int i = 0; i < D; i++) grad_pos[(size_t)n * D + i] = gp[i];
     }
 }
 
@@ -334,11 +353,24 @@ k_enc_double_backward(EncParams p, const float* __restrict__ pos, const float2* 
                       const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ window,
                       const float* __restrict__ gg_pos, const float* __restrict__ grad_out, float* __restrict__ grad_lattice,
                       float* __restrict__ grad_grad_out) {
+    extern __shared__ float smem_dyn[];
     __shared__ LevelConsts lc;
     load_level_consts<D>(lc, scale, shift, window, p.L);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int stride = p.C + 1;
+    float* gtile = smem_dyn;                         // staged grad_out block
+    float* otile = smem_dyn + 32 * stride;           // grad_grad_out block, written out coalesced
+    const int row0 = blockIdx.x * 32;
+    const int rows = min(32, p.N - row0);
+    if (LATTICE) {
+        const float* src = grad_out + (size_t)row0 * p.C;
+        for (int e = threadIdx.x; e < 32 * p.C; e += kEncThreads) {
+            int r = e / p.C, c = e - r * p.C;
+            gtile[r * stride + c] = (r < rows) ? src[e] : 0.0f;
+        }
+    }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int n = blockIdx.x * kEncThreads + threadIdx.x;
+    const int n = row0 + lane;
     const bool valid = n < p.N;
     float x[D], u[D];
 #pragma unroll
@@ -346,9 +378,8 @@ k_enc_double_backward(EncParams p, const float* __restrict__ pos, const float2* 
         x[i] = valid ? pos[(size_t)n * D + i] : 0.0f;
         u[i] = valid ? gg_pos[(size_t)n * D + i] : 0.0f;
     }
-    const size_t row = (size_t)(valid ? n : 0) * p.C;
-#pragma unroll 1
-    for (int l = 0; l < p.L; l++) {
+#pragma unroll 2
+    for (int l = warp; l < p.L; l += kGroups) {
         float cf[D], dcf[D], elevated[D + 1], d_elev[D + 1];
 #pragma unroll
         for (int i = 0; i < D; i++) {
@@ -380,10 +411,11 @@ k_enc_double_backward(EncParams p, const float* __restrict__ pos, const float2* 
                 a0 = fmaf(v.x, c, a0);
                 a1 = fmaf(v.y, c, a1);
             }
-            if (valid) *reinterpret_cast<float2*>(grad_grad_out + row + 2 * l) = make_float2(a0, a1);
+            otile[lane * stride + 2 * l] = a0;
+            otile[lane * stride + 2 * l + 1] = a1;
         }
         if (LATTICE) {
-            float2 g = valid ? *reinterpret_cast<const float2*>(grad_out + row + 2 * l) : make_float2(0.f, 0.f);
+            float2 g = make_float2(gtile[lane * stride + 2 * l], gtile[lane * stride + 2 * l + 1]);
             float* gtab = grad_lattice + (size_t)l * p.T * 2;
 #pragma unroll
             for (int r = 0; r <= D; r++) {
@@ -396,14 +428,23 @@ k_enc_double_backward(EncParams p, const float* __restrict__ pos, const float2* 
             }
         }
     }
-    if (GOUT && valid && p.concat) {
-        const int base = 2 * p.L;
-        for (int c = base; c < p.C; c++) {
-            int d = c - base;
-            float val = 0.0f;
+    if (GOUT) {
+        if (p.concat && warp == kGroups - 1) {
+            const int base = 2 * p.L;
+            for (int c = base; c < p.C; c++) {
+                int d = c - base;
+                float val = 0.0f;
 #pragma unroll
-            for (int i = 0; i < D; i++) if (i == d) val = u[i] * p.points_scaling;
-            grad_grad_out[row + c] = val;
+                for (int i = 0; i < D; i++) if (i == d) val = u[i] * p.points_scaling;
+                otile[lane * stride + c] = val;
+            }
+        }
+        __syncthreads();
+        float* dst = grad_grad_out + (size_t)row0 * p.C;
+        const int total = rows * p.C;
+        for (int e = threadIdx.x; e < total; e += kEncThreads) {
+            int r = e / p.C, c = e - r * p.C;
+            dst[e] = otile[r * stride + c];
         }
     }
 }
@@ -429,8 +470,8 @@ int psdf_enc_forward(int N, int D, int L, int F, int T, const float* pos, const 
     int rc = make_params(p, N, D, L, F, T, concat_points, points_scaling);
     if (rc) return rc;
     if (N == 0) return PSDF_OK;
-    int blocks = div_up(N, kEncThreads);
-    size_t smem = (size_t)(kEncThreads / 32) * 32 * (p.C + 1) * sizeof(float);
+    int blocks = div_up(N, 32);
+    size_t smem = (size_t)32 * (p.C + 1) * sizeof(float);
     const float2* lat = reinterpret_cast<const float2*>(lattice);
     if (D == 3) k_enc_forward<3><<<blocks, kEncThreads, smem, ST>>>(p, pos, lat, scale_factor, shift, window, out);
     else k_enc_forward<4><<<blocks, kEncThreads, smem, ST>>>(p, pos, lat, scale_factor, shift, window, out);
@@ -445,10 +486,11 @@ int psdf_enc_backward(int N, int D, int L, int F, int T, const float* pos, const
     int rc = make_params(p, N, D, L, F, T, concat_points, points_scaling);
     if (rc) return rc;
     if (N == 0 || (!grad_lattice && !grad_pos)) return PSDF_OK;
-    int blocks = div_up(N, kEncThreads);
+    int blocks = div_up(N, 32);
+    size_t smem = (size_t)32 * (p.C + 1) * sizeof(float);
     const float2* lat = reinterpret_cast<const float2*>(lattice);
 #define LAUNCH_BWD(DD, LA, PO) \
-    k_enc_backward<DD, LA, PO><<<blocks, kEncThreads, 0, ST>>>(p, pos, lat, scale_factor, shift, window, grad_out, grad_lattice, grad_pos)
+    k_enc_backward<DD, LA, PO><<<blocks, kEncThreads, smem, ST>>>(p, pos, lat, scale_factor, shift, window, grad_out, grad_lattice, grad_pos)
     if (D == 3) {
         if (grad_lattice && grad_pos) LAUNCH_BWD(3, true, true);
         else if (grad_lattice) LAUNCH_BWD(3, true, false);
@@ -469,10 +511,11 @@ int psdf_enc_double_backward(int N, int D, int L, int F, int T, const float* pos
     int rc = make_params(p, N, D, L, F, T, concat_points, points_scaling);
     if (rc) return rc;
     if (N == 0 || (!grad_lattice && !grad_grad_out)) return PSDF_OK;
-    int blocks = div_up(N, kEncThreads);
+    int blocks = div_up(N, 32);
+    size_t smem = (size_t)2 * 32 * (p.C + 1) * sizeof(float);
     const float2* lat = reinterpret_cast<const float2*>(lattice);
 #define LAUNCH_DBL(DD, LA, GO)                                                                                                  \
-    k_enc_double_backward<DD, LA, GO><<<blocks, kEncThreads, 0, ST>>>(p, pos, lat, scale_factor, shift, window, gg_pos, grad_out, \
+    k_enc_double_backward<DD, LA, GO><<<blocks, kEncThreads, smem, ST>>>(p, pos, lat, scale_factor, shift, window, gg_pos, grad_out, \
                                                                      grad_lattice, grad_grad_out)
     if (D == 3) {
         if (grad_lattice && grad_grad_out) LAUNCH_DBL(3, true, true);

@@ -165,6 +165,8 @@ __device__ __forceinline__ void store8(uint8_t* a_hi, uint8_t* a_lo, int row, in
     *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+__device__ int g_desc_swap = 0;
+
 // issue the three split products of one [128 x Kp] x [Np x Kp]^T GEMM into TMEM (single thread)
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
                                            const uint8_t* w_lo, int Kp, int Np) {
@@ -173,8 +175,12 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a_hi,
     const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo), wh = umma::smem_u32(w_hi), wl = umma::smem_u32(w_lo);
     for (int kk = 0; kk < Kp / 16; kk++) {
         uint32_t ko = kk * 2 * kLBO;      // 16 bf16 = 2 core matrices along K
-        uint64_t dah = umma::make_desc(ah + ko, kLBO, kSBO_A), dal = umma::make_desc(al + ko, kLBO, kSBO_A);
-        uint64_t dwh = umma::make_desc(wh + ko, kLBO, sbo_w), dwl = umma::make_desc(wl + ko, kLBO, sbo_w);
+        // g_desc_swap: which of the two descriptor offset fields is the K-direction stride (self-test probes this)
+        const bool sw = g_desc_swap != 0;
+        uint64_t dah = sw ? umma::make_desc(ah + ko, kSBO_A, kLBO) : umma::make_desc(ah + ko, kLBO, kSBO_A);
+        uint64_t dal = sw ? umma::make_desc(al + ko, kSBO_A, kLBO) : umma::make_desc(al + ko, kLBO, kSBO_A);
+        uint64_t dwh = sw ? umma::make_desc(wh + ko, sbo_w, kLBO) : umma::make_desc(wh + ko, kLBO, sbo_w);
+        uint64_t dwl = sw ? umma::make_desc(wl + ko, sbo_w, kLBO) : umma::make_desc(wl + ko, kLBO, sbo_w);
         umma::mma_bf16(tmem_d, dah, dwh, idesc, kk > 0 ? 1u : 0u);
         umma::mma_bf16(tmem_d, dah, dwl, idesc, 1u);
         umma::mma_bf16(tmem_d, dal, dwh, idesc, 1u);
@@ -480,6 +486,10 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
     }
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
+}
+
+int psdf_debug_set_desc_swap(int swap) {
+    return cudaMemcpyToSymbol(g_desc_swap, &swap, sizeof(int)) == cudaSuccess ? PSDF_OK : PSDF_ERR_LAUNCH;
 }
 
 int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream) {

@@ -1,0 +1,60 @@
+"""Fused evaluation of the SDF model (encoding + MLP in one tcgen05 kernel, csrc/fused_sdf.cu).
+
+`FusedSDF(model_sdf)` wraps a `models.SDF` and evaluates sdf / d sdf/dx / geometric feature without
+materialising encoded features or hidden activations in HBM. It is used where no parameter gradient is
+needed: SDF importance sampling, the occupancy-grid refresh, sphere tracing and normals. Training-time
+evaluations that need parameter gradients go through the differentiable modules (models.SDF).
+"""
+import torch
+
+from ._lib import call, load_library
+
+
+class FusedSDF:
+    def __init__(self, model_sdf):
+        self.model = model_sdf
+        enc = model_sdf.encoding
+        lin = [m for m in model_sdf.mlp_sdf if isinstance(m, torch.nn.Linear)]
+        if len(lin) != 4:
+            raise RuntimeError("FusedSDF supports the 4-linear-layer SDF MLP of the reference (models.py:153-161)")
+        if enc.pos_dim != 3 or enc.nr_feat_per_level != 2 or not enc.concat_points or enc.nr_levels % 4 != 0:
+            raise RuntimeError("FusedSDF needs pos_dim 3, 2 features per level, concat_points and nr_levels % 4 == 0")
+        self.lin = lin
+        self.in_dim = lin[0].in_features
+        self.hidden = lin[0].out_features
+        self.out_dim = lin[3].out_features
+        if self.in_dim != enc.output_dims() or self.hidden % 16 != 0 or self.hidden > 64 or self.out_dim > 64 or self.in_dim > 64:
+            raise RuntimeError("unsupported MLP shape for the fused kernel")
+        lib = load_library()
+        self.blob = torch.empty(int(lib.psdf_sdf_mlp_blob_bytes(self.in_dim, self.hidden, self.out_dim)), dtype=torch.uint8,
+                                device=enc.lattice_values.device)
+        self._versions = None
+        self.repack()
+
+    def _cur_versions(self):
+        return tuple(p._version for l in self.lin for p in (l.weight, l.bias))
+
+    def repack(self):
+        """weights -> tensor-core operand blob (call after every optimizer step; cheap, one small kernel)"""
+        l = self.lin
+        call("psdf_sdf_mlp_pack", self.in_dim, self.hidden, self.out_dim, l[0].weight.detach(), l[0].bias.detach(), l[1].weight.detach(),
+             l[1].bias.detach(), l[2].weight.detach(), l[2].bias.detach(), l[3].weight.detach(), l[3].bias.detach(), self.blob)
+        self._versions = self._cur_versions()
+
+    @torch.no_grad()
+    def __call__(self, points, iter_nr, with_gradient=False, with_geom=True):
+        """-> (sdf [N,1], gradient [N,3] or None, geom_feat [N,out-1] or None)"""
+        if self._versions != self._cur_versions():
+            self.repack()
+        m, enc = self.model, self.model.encoding
+        m.last_iter_nr = iter_nr
+        pts = points.detach().contiguous()
+        N = pts.shape[0]
+        dev = pts.device
+        sdf = torch.empty(N, 1, device=dev)
+        grad = torch.empty(N, 3, device=dev) if with_gradient else None
+        geom = torch.empty(N, self.out_dim - 1, device=dev) if (with_geom and self.out_dim > 1) else None
+        window = m.window(iter_nr).view(-1).contiguous()
+        call("psdf_sdf_fused_forward", N, enc.nr_levels, enc.capacity, pts, enc.lattice_values.detach(), enc.scale_factor,
+             enc.shift_tensor(), window, enc.concat_points_scaling, self.hidden, self.out_dim, self.blob, sdf, grad, geom)
+        return sdf, grad, geom

@@ -1,0 +1,102 @@
+"""GPU tests of the tcgen05 path: the raw tensor-core GEMM self test (descriptor / layout check) and the fused
+encoding+MLP SDF kernel against (a) the CPU oracle and (b) the unfused differentiable model. Tolerance: the
+north star's 1e-3 relative; the bf16x2 split keeps it ~1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import encoding_oracle as eo
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _gemm_err(N, K):
+    from permuto_sdf_b200 import call
+    torch.manual_seed(N * 100 + K)
+    A = torch.randn(128, K, device="cuda")
+    B = torch.randn(N, K, device="cuda")
+    D = torch.zeros(128, N, device="cuda")
+    call("psdf_debug_umma_gemm", N, K, A, B, D)
+    torch.cuda.synchronize()
+    return rel(D, A.double() @ B.double().t())
+
+
+def test_descriptor_convention_probe(cuda):
+    """the library default must be the working convention; the probe prints what the other one gives"""
+    from permuto_sdf_b200 import load_library
+    lib = load_library()
+    errs = {}
+    for sw in (1, 0):
+        assert lib.psdf_debug_set_desc_swap(sw) == 0
+        errs[sw] = _gemm_err(64, 64)
+    print("umma descriptor probe: rel err with LBO=K-stride (default): %g, swapped: %g" % (errs[0], errs[1]))
+    assert errs[0] < 5e-5, "default descriptor convention is wrong: %s" % errs
+
+
+@pytest.mark.parametrize("N,K", [(64, 64), (48, 64), (64, 48), (16, 16), (33, 36)])
+def test_umma_gemm_self_test(cuda, N, K):
+    from permuto_sdf_b200 import call
+    torch.manual_seed(N * 100 + K)
+    A = torch.randn(128, K, device="cuda")
+    B = torch.randn(N, K, device="cuda")
+    D = torch.zeros(128, N, device="cuda")
+    call("psdf_debug_umma_gemm", N, K, A, B, D)
+    torch.cuda.synchronize()
+    ref = (A.double() @ B.double().t())
+    err = rel(D, ref)
+    assert err < 5e-5, "tensor-core GEMM mismatch (rel err %g): descriptor/layout problem" % err
+
+
+@pytest.mark.parametrize("L,hidden,N", [(16, 64, 5000), (8, 32, 1000), (24, 32, 777), (4, 64, 128)])
+def test_fused_sdf_matches_oracle_and_model(cuda, L, hidden, N):
+    from permuto_sdf import Sphere
+    from permuto_sdf_b200.fused import FusedSDF
+    from permuto_sdf_b200.models import SDF
+    torch.manual_seed(L)
+    m = SDF(3, Sphere(0.5, [0, 0, 0]), 32, 10000, nr_levels=L, capacity=2 ** 16, hidden=hidden).to("cuda")
+    with torch.no_grad():
+        m.encoding.lattice_values.normal_(0, 0.3)          # non-trivial features
+    f = FusedSDF(m)
+    pos = ((torch.rand(N, 3) - 0.5) * 0.9)
+    it = 3000
+    sdf, grad, geom = f(pos.cuda(), it, with_gradient=True)
+    sdf_v, none_g, geom_v = f(pos.cuda(), it, with_gradient=False)
+    assert none_g is None and torch.equal(sdf, sdf_v) or rel(sdf_v, sdf) < 1e-6
+    # (b) unfused differentiable model
+    s1, g1, f1 = m.get_sdf_and_gradient(pos.cuda().clone(), it)
+    assert rel(sdf, s1) < 1e-3 and rel(grad, g1) < 1e-3 and rel(geom, f1) < 1e-3
+    # (a) CPU oracle
+    enc = m.encoding
+    lin = [l for l in m.mlp_sdf if isinstance(l, torch.nn.Linear)]
+    W = [l.weight.detach().cpu() for l in lin]; Bs = [l.bias.detach().cpu() for l in lin]
+    window = eo.coarse2fine(L, 0.3 + 0.7 * it / 10000)
+    s0, g0, f0 = eo.sdf_and_gradient(pos, enc.lattice_values.detach().cpu(), enc.scale_factor.cpu(), enc.random_shift_per_level.detach().cpu(),
+                                     window, W, Bs, True, 1e-3)
+    e = (rel(sdf, s0), rel(grad, g0), rel(geom, f0))
+    assert max(e) < 1e-3, e
+    # the blob follows weight updates
+    with torch.no_grad():
+        lin[3].bias += 0.25
+    s2, _, _ = f(pos.cuda(), it)
+    assert rel(s2, s0 + 0.25) < 1e-3
+
+
+def test_fused_sdf_large_and_ragged(cuda):
+    from permuto_sdf import Sphere
+    from permuto_sdf_b200.fused import FusedSDF
+    from permuto_sdf_b200.models import SDF
+    torch.manual_seed(0)
+    m = SDF(3, Sphere(0.5, [0, 0, 0]), 32, 1, nr_levels=16, capacity=2 ** 18, hidden=64).to("cuda")
+    f = FusedSDF(m)
+    for N in (0, 1, 127, 129, 65536 + 5):
+        pos = (torch.rand(N, 3, device="cuda") - 0.5)
+        sdf, grad, geom = f(pos, 10, with_gradient=True)
+        assert sdf.shape == (N, 1) and grad.shape == (N, 3) and geom.shape == (N, 32)
+        if N:
+            s1, g1, f1 = m.get_sdf_and_gradient(pos.clone(), 10)
+            assert rel(sdf, s1) < 1e-3 and rel(grad, g1) < 1e-3 and rel(geom, f1) < 1e-3
