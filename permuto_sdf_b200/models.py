@@ -116,9 +116,19 @@ class SDF(torch.nn.Module):
     def window(self, iter_nr):
         return self.c2f(map_range_val(iter_nr, 0.0, self.nr_iters_for_c2f, 0.3, 1.0))
 
+    def enable_fused_inference(self):
+        """route gradient-free evaluations (importance sampling, occupancy refresh, sphere tracing) through the fused
+        encoding+MLP tcgen05 kernel (csrc/fused_sdf.cu); differentiable calls keep using the modular path"""
+        from .fused import FusedSDF
+        self.fused = FusedSDF(self)
+        return self.fused
+
     def forward(self, points, iter_nr):
         assert points.shape[1] == self.in_channels, "points should be N x in_channels"
         self.last_iter_nr = iter_nr
+        if getattr(self, "fused", None) is not None and not torch.is_grad_enabled():
+            sdf, _, geom = self.fused(points, iter_nr, with_gradient=False, with_geom=self.geom_feat_size_out != 0)
+            return sdf, geom
         feat = self.encoding(points, self.window(iter_nr).view(-1))
         y = self.mlp_sdf(feat)
         if self.geom_feat_size_out != 0:

@@ -178,7 +178,9 @@ def sphere_trace(nr_sphere_traces, ray_origins, ray_dirs, model, return_gradient
         conv_u = torch.logical_or(newly, torch.logical_not(within.view(-1)))
         converged[sel] = torch.logical_or(converged[sel].view(-1), conv_u).view(-1, 1)
         pts[sel] = pos_u
-    if return_gradients:
+    if return_gradients and getattr(model, "fused", None) is not None:
+        sdf, grads, geom = model.fused(pts, model.last_iter_nr, with_gradient=True)      # forward-mode normal, one kernel
+    elif return_gradients:
         with torch.enable_grad():
             sdf, grads, geom = model.get_sdf_and_gradient(pts.detach().clone(), model.last_iter_nr)
             grads = grads.detach()[:, 0:3]
@@ -211,8 +213,9 @@ class Trainer:
     per-iteration step of train_permuto_sdf.py:311-422 (after sphere init), with `--with_mask` semantics."""
 
     def __init__(self, hyperparams=None, nr_levels=24, capacity=2 ** 18, sdf_hidden=32, nr_images=8, occupancy_resolution=256,
-                 seed=0, with_colorcal=True, optimizer="adamw"):
+                 seed=0, with_colorcal=True, optimizer="adamw", fused_inference=True):
         torch.manual_seed(seed)
+        self._fused_inference = fused_inference
         self.hp = hyperparams or HyperParams()
         self.aabb = Sphere(0.5, [0, 0, 0])
         hp = self.hp
@@ -221,6 +224,8 @@ class Trainer:
         self.model_bg = None if hp.with_mask else NerfHash(4, self.aabb, hp.background_nr_iters_for_c2f, nr_levels, capacity).to("cuda")
         self.model_colorcal = Colorcal(nr_images, 0) if (hp.use_color_calibration and with_colorcal) else None
         self.occupancy_grid = OccupancyGrid(occupancy_resolution, 1.0, [0, 0, 0]) if hp.use_occupancy_grid else None
+        if fused_inference and nr_levels % 4 == 0 and sdf_hidden % 16 == 0 and sdf_hidden <= 64 and self.model_sdf.encoding.output_dims() <= 64:
+            self.model_sdf.enable_fused_inference()
         groups = [{"params": list(self.model_sdf.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_sdf"}]
         if self.model_bg is not None:
             groups.append({"params": list(self.model_bg.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_bg"})

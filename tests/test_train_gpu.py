@@ -44,6 +44,11 @@ def test_sdf_and_gradient_match_oracle(trainer):
     # finite-difference variant of the reference API
     s1, g1, _ = m.get_sdf_and_gradient(pos.cuda(), it, method="finite_difference")
     assert rel(s1, s0) < 1e-3
+    # gradient-free evaluations are routed through the fused tcgen05 kernel
+    assert getattr(m, "fused", None) is not None
+    with torch.no_grad():
+        s2, f2 = m(pos.cuda(), it)
+    assert rel(s2, s0) < 1e-3 and rel(f2, f0) < 1e-3
 
 
 def test_neus_weights_match_oracle(trainer):
