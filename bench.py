@@ -160,7 +160,8 @@ def run_ours(args):
     hp.max_nr_samples_per_ray = SAMPLES_PER_RAY - 2 * 16
     hp.nr_samples_imp_sampling = 16
     hp.nr_rays = NR_RAYS
-    tr = Trainer(hp, nr_levels=16, capacity=2 ** 18, sdf_hidden=64, nr_images=8, occupancy_resolution=256, seed=0)
+    tr = Trainer(hp, nr_levels=16, capacity=2 ** 18, sdf_hidden=64, nr_images=8, occupancy_resolution=256, seed=0,
+                 fused_inference=not args.modular, fused_training=not args.modular)
     tr.set_analytic_scene()
     tr.iter_nr = 20000          # past coarse-to-fine: all 16 levels active, cos-anneal half way
     H, W, f = 600, 800, 1000.0
@@ -298,6 +299,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--modular", action="store_true", help="drop-in API path only (encoding kernels + torch MLP), no fused tcgen05 kernels")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -171,10 +171,17 @@ int psdf_sdf_mlp_pack(int in_dim, int hidden, int out_dim, const float* W0, cons
 int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
                            const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, float* sdf,
                            float* grad, float* geom, void* stream);
+/* Training backward of psdf_sdf_fused_forward (double backward of encoding + MLP in one tcgen05 kernel):
+ * upstream gradients g_sdf [N], g_grad [N,3], g_geom [N,out_dim-1] (any may be NULL) -> grad_lattice (+=), bias gradients
+ * gb_l [N_l] (+=) and the spill matrices zcat_l [2N, pad16(N_l)], acat_l [2N, pad16(K_l)] with
+ * dW_l = (zcat_l^T @ acat_l)[:N_l, :K_l]. Replaces loss.backward() through SDF.get_sdf_and_gradient (models.py:199-259). */
+int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
+                            const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, const float* g_sdf,
+                            const float* g_grad, const float* g_geom, float* grad_lattice, float* zcat0, float* zcat1, float* zcat2,
+                            float* zcat3, float* acat0, float* acat1, float* acat2, float* acat3, float* gb0, float* gb1, float* gb2,
+                            float* gb3, void* stream);
 /* self-test of the tensor-core path: D[128,N] = A[128,K] * B[N,K]^T (N,K <= 64) */
 int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream);
-/* debug: choose which shared-memory-descriptor offset field carries the K-direction stride (0 = LBO, default) */
-int psdf_debug_set_desc_swap(int swap);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,8 @@ struct GridGeom {
     int V;            // voxels per dim (power of two)
     float extent;     // world size of the cube
     float tx, ty, tz; // translation of the cube centre
+    float inv_extent; // 1/extent when extent is a power of two (x/extent == x*inv exactly), else 0 -> IEEE division
+    float inv_V;      // 1/V, exact: V is a power of two
 };
 
 #ifdef __CUDACC__
@@ -101,9 +103,13 @@ struct GridGeom {
 // Reference op order (SASS of check_occupancy_gpu): sub, IEEE div, add .5, mul V, cvt.rzi.u32 (saturating).
 __device__ __forceinline__ int pos_to_voxel(float px, float py, float pz, const GridGeom& g) {
     float Vf = (float)g.V;
-    float x = __fmul_rn(__fadd_rn(__fdiv_rn(__fsub_rn(px, g.tx), g.extent), 0.5f), Vf);
-    float y = __fmul_rn(__fadd_rn(__fdiv_rn(__fsub_rn(py, g.ty), g.extent), 0.5f), Vf);
-    float z = __fmul_rn(__fadd_rn(__fdiv_rn(__fsub_rn(pz, g.tz), g.extent), 0.5f), Vf);
+    // division by a power of two is exact, so the multiply below is bit-identical to the reference's IEEE division
+    float qx = __fsub_rn(px, g.tx), qy = __fsub_rn(py, g.ty), qz = __fsub_rn(pz, g.tz);
+    if (g.inv_extent != 0.0f) { qx = __fmul_rn(qx, g.inv_extent); qy = __fmul_rn(qy, g.inv_extent); qz = __fmul_rn(qz, g.inv_extent); }
+    else { qx = __fdiv_rn(qx, g.extent); qy = __fdiv_rn(qy, g.extent); qz = __fdiv_rn(qz, g.extent); }
+    float x = __fmul_rn(__fadd_rn(qx, 0.5f), Vf);
+    float y = __fmul_rn(__fadd_rn(qy, 0.5f), Vf);
+    float z = __fmul_rn(__fadd_rn(qz, 0.5f), Vf);
     return (int)morton3(__float2uint_rz(x), __float2uint_rz(y), __float2uint_rz(z));
 }
 
@@ -147,7 +153,7 @@ __device__ __forceinline__ float dda_step(float px, float py, float pz, float dx
     float ty = fabsf(dda_axis(py, dy, iy, Vf));
     float tz = fabsf(dda_axis(pz, dz, iz, Vf));
     float t = fminf(fminf(tx, ty), tz);
-    return fmaxf(__fdiv_rn(t, Vf), 0.0f);
+    return fmaxf(__fmul_rn(t, 1.0f / Vf), 0.0f);   // V is a power of two: t / V == t * (1/V) exactly
 }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fmaxf(lo, fminf(x, hi)); }

@@ -1,0 +1,189 @@
+// Shared pieces of the fused encoding + MLP kernels (fused_sdf.cu: forward / inference, fused_sdf_bwd.cu: training
+// backward): MLP operand-blob geometry, permutohedral simplex helpers for D = 3, GELU and its derivatives, operand
+// tile stores (bf16 hi/lo split in the UMMA core-matrix layout) and the split-product GEMM issue.
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace psdf_fused {
+using namespace psdf;
+constexpr int kTile = 128;
+constexpr int kMaxLevels = 32;
+constexpr int kNL = 4;                 // linear layers of the SDF MLP
+constexpr int kATileBytes = 128 * 64 * 2;   // one bf16 operand tile [128 x 64]
+constexpr int kLBO = 128;
+constexpr int kSBO_A = 1024;           // 8 core matrices (K = 64) per 8-row group
+
+struct MlpGeom {
+    int K[kNL], N[kNL];        // true dims
+    int Kp[kNL], Np[kNL];      // padded dims (K % 16 == 0, N % 16 == 0)
+    int w_hi[kNL], w_lo[kNL], bias[kNL];   // byte offsets in the forward blob [0, total)
+    int total;
+    int t_hi[kNL], t_lo[kNL];  // byte offsets of the transposed weights W_l^T ([Kp rows][Np cols]) in [total, total + total_t)
+    int total_t;
+};
+__host__ __device__ inline int pad16(int v) { return (v + 15) & ~15; }
+inline MlpGeom make_geom(int in_dim, int hidden, int out_dim) {
+    MlpGeom g;
+    int dims[kNL + 1] = {in_dim, hidden, hidden, hidden, out_dim};
+    int off = 0;
+    for (int l = 0; l < kNL; l++) {
+        g.K[l] = dims[l]; g.N[l] = dims[l + 1];
+        g.Kp[l] = pad16(dims[l]); g.Np[l] = pad16(dims[l + 1]);
+        int wbytes = g.Np[l] * g.Kp[l] * 2;
+        g.w_hi[l] = off; off += wbytes;
+        g.w_lo[l] = off; off += wbytes;
+        g.bias[l] = off; off += g.Np[l] * 4;
+    }
+    g.total = (off + 127) & ~127;
+    off = 0;
+    for (int l = 0; l < kNL; l++) {
+        int wbytes = g.Np[l] * g.Kp[l] * 2;
+        g.t_hi[l] = off; off += wbytes;
+        g.t_lo[l] = off; off += wbytes;
+    }
+    g.total_t = (off + 127) & ~127;
+    return g;
+}
+
+// weights [N][K] fp32 (torch.nn.Linear layout) -> hi/lo bf16 in the UMMA K-major core-matrix layout + fp32 bias;
+// second half of the blob: the same weights transposed (rows = input features, K = output features) for the
+// backward GEMMs dA = dZ * W
+static __global__ void k_pack_mlp(MlpGeom g, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
+                                  const float* b2, const float* W3, const float* b3, uint8_t* blob) {
+    const float* W[kNL] = {W0, W1, W2, W3};
+    const float* B[kNL] = {b0, b1, b2, b3};
+    int l = blockIdx.y;
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = g.Np[l] * g.Kp[l];
+    if (e < total) {
+        int n = e / g.Kp[l], k = e - n * g.Kp[l];
+        float v = (n < g.N[l] && k < g.K[l]) ? W[l][n * g.K[l] + k] : 0.0f;
+        __nv_bfloat16 hi, lo;
+        umma::split_bf16(v, hi, lo);
+        int sbo = (g.Kp[l] / 8) * kLBO;
+        int off = (n / 8) * sbo + (k / 8) * kLBO + (n % 8) * 16 + (k % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(blob + g.w_hi[l] + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(blob + g.w_lo[l] + off) = lo;
+        // transposed copy: row = k (input feature), reduction index = n (output feature)
+        int sbo_t = (g.Np[l] / 8) * kLBO;
+        int off_t = (k / 8) * sbo_t + (n / 8) * kLBO + (k % 8) * 16 + (n % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(blob + g.total + g.t_hi[l] + off_t) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(blob + g.total + g.t_lo[l] + off_t) = lo;
+    }
+    if (e < g.Np[l]) reinterpret_cast<float*>(blob + g.bias[l])[e] = (e < g.N[l]) ? B[l][e] : 0.0f;
+}
+
+// ---------------------------------------------------------------------------------------------- lattice helpers (D = 3)
+struct Simplex3 { int rem0[4]; int rank[4]; float bary[5]; };
+__device__ __forceinline__ void elevate3(const float* cf, float* e) {
+    float sm = 0.0f;
+#pragma unroll
+    for (int i = 3; i > 0; i--) { e[i] = __fmaf_rn(-(float)i, cf[i - 1], sm); sm = __fadd_rn(sm, cf[i - 1]); }
+    e[0] = sm;
+}
+__device__ __forceinline__ void locate3(const float* e, Simplex3& s) {
+    int sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float v = __fmul_rn(e[i], 0.25f);
+        float up = __fmul_rn(ceilf(v), 4.0f), down = __fmul_rn(floorf(v), 4.0f);
+        s.rem0[i] = (__fsub_rn(up, e[i]) < __fsub_rn(e[i], down)) ? (int)up : (int)down;
+        sum += s.rem0[i];
+        s.rank[i] = 0;
+    }
+    sum /= 4;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        float di = __fsub_rn(e[i], (float)s.rem0[i]);
+#pragma unroll
+        for (int j = i + 1; j < 4; j++) { if (di < __fsub_rn(e[j], (float)s.rem0[j])) s.rank[i]++; else s.rank[j]++; }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        s.rank[i] += sum;
+        if (s.rank[i] < 0) { s.rank[i] += 4; s.rem0[i] += 4; }
+        else if (s.rank[i] > 3) { s.rank[i] -= 4; s.rem0[i] -= 4; }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; i++) s.bary[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float delta = __fmul_rn(__fsub_rn(e[i], (float)s.rem0[i]), 0.25f);
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            if (r == 3 - s.rank[i]) s.bary[r] = __fadd_rn(s.bary[r], delta);
+            if (r == 4 - s.rank[i]) s.bary[r] = __fsub_rn(s.bary[r], delta);
+        }
+    }
+    s.bary[0] = __fadd_rn(s.bary[0], __fadd_rn(1.0f, s.bary[4]));
+}
+__device__ __forceinline__ unsigned vindex3(const Simplex3& s, int r, unsigned cap_mask, unsigned T) {
+    unsigned h = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        int key = s.rem0[i] + r;
+        if (s.rank[i] > 3 - r) key -= 4;
+        h += (unsigned)key;
+        h *= 2531011u;
+    }
+    return cap_mask ? (h & cap_mask) : (h % T);
+}
+
+__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_d(float z) {
+    float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
+    float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
+    return cdf + z * pdf;
+}
+
+struct FusedParams {
+    int N, L, T;
+    unsigned cap_mask;
+    float points_scaling;
+    int in_dim;          // (L + E) * 2 feature columns
+    MlpGeom g;
+};
+
+struct LevelC { float scale[kMaxLevels * 4]; float shift[kMaxLevels * 4]; float window[kMaxLevels]; };
+
+// store 8 consecutive K values of one row into a hi/lo operand tile pair (one 16-byte core-matrix row each)
+__device__ __forceinline__ void store8(uint8_t* a_hi, uint8_t* a_lo, int row, int kcore, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        umma::split_bf16(v[2 * i], h0, l0);
+        umma::split_bf16(v[2 * i + 1], h1, l1);
+        h[i] = umma::pack2(h0, h1);
+        l[i] = umma::pack2(l0, l1);
+    }
+    int off = (row >> 3) * kSBO_A + kcore * kLBO + (row & 7) * 16;
+    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ float gelu_d2(float z) {   // d/dz [Phi(z) + z phi(z)] = phi(z) (2 - z^2)
+    return 0.3989422804014327f * __expf(-0.5f * z * z) * (2.0f - z * z);
+}
+
+// issue the three split products of one [128 x Kp] x [Np x Kp]^T GEMM into TMEM (single thread).
+// Descriptor convention validated on B200 by tests/test_fused_gpu.py::test_umma_gemm_self_test: the first offset field
+// (LBO) is the stride between core matrices adjacent along K, the second (SBO) between 8-row groups.
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
+                                           const uint8_t* w_lo, int Kp, int Np) {
+    const uint32_t idesc = umma::make_idesc(128, Np, umma::kFmtBF16);
+    const uint32_t sbo_w = (Kp / 8) * kLBO;
+    const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo), wh = umma::smem_u32(w_hi), wl = umma::smem_u32(w_lo);
+    for (int kk = 0; kk < Kp / 16; kk++) {
+        uint32_t ko = kk * 2 * kLBO;      // 16 bf16 = 2 core matrices along K
+        uint64_t dah = umma::make_desc(ah + ko, kLBO, kSBO_A), dal = umma::make_desc(al + ko, kLBO, kSBO_A);
+        uint64_t dwh = umma::make_desc(wh + ko, kLBO, sbo_w), dwl = umma::make_desc(wl + ko, kLBO, sbo_w);
+        umma::mma_bf16(tmem_d, dah, dwh, idesc, kk > 0 ? 1u : 0u);
+        umma::mma_bf16(tmem_d, dah, dwl, idesc, 1u);
+        umma::mma_bf16(tmem_d, dal, dwh, idesc, 1u);
+    }
+}
+
+
+}  // namespace psdf_fused

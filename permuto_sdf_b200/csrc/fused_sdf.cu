@@ -1,7 +1,6 @@
 // Fused permutohedral encoding + SDF MLP for sm_100a: positions in, {sdf, d sdf/d x, geometric feature} out;
 // the 36..52 encoded features and every hidden activation stay on chip (registers -> shared memory operand
-// tiles -> tcgen05 tensor cores -> TMEM accumulators -> registers). Replaces, for inference-type evaluations
-// (importance sampling, occupancy refresh, sphere tracing, normals), the reference's chain
+// tiles -> tcgen05 tensor cores -> TMEM accumulators -> registers). Replaces the reference's chain
 //   permutohedral_encoding.forward -> 4x cuBLAS SGEMM + 3x GELU kernels (+ autograd.grad for the normal)
 // of SDF.forward / SDF.get_sdf_and_gradient (permuto_sdf_py/models/models.py:176-259).
 //
@@ -14,181 +13,25 @@
 // the same weights ( tz_l = W_l ta_{l-1}, ta_l = gelu'(z_l) * tz_l ), their level-0 input being d feat / d x_j,
 // which is exact because barycentric weights are piecewise linear in x.
 //
-// Work mapping: one CTA = 128 threads = one 128-sample tile = the M of the MMA; thread t owns sample t in the
-// encoder and row t of every accumulator (TMEM lane t). Weights (hi+lo, pre-packed in the UMMA core-matrix
-// layout by k_pack_mlp) are fetched once per CTA with one cp.async.bulk (TMA) and stay resident; CTAs are
-// persistent over tiles. Value-only evaluation uses 89 KB smem (2 CTAs/SM), value+tangents 185 KB (1 CTA/SM).
-#include "common.cuh"
-#include "umma.cuh"
+// Work mapping: one CTA = one 128-sample tile = the M of the MMA, 512 threads = 4 groups x 128 rows.
+//   encoder : thread (row, g) computes the 16-byte operand cores g, g+4, ... (4 lattice levels = 8 features each)
+//             of its sample for all streams -> 16 gathers per thread in flight at L = 16, 16 warps per SM;
+//   MMA     : thread 0 issues S streams x (K/16) x 3 tcgen05.mma, one tcgen05.commit -> mbarrier;
+//   epilogue: thread (row, g) owns accumulator columns [16g, 16g+16) of row `row` (TMEM lane row) of every stream:
+//             tcgen05.ld, bias, GELU / GELU', bf16 hi/lo split, 16-byte core stores for the next layer.
+// Weights (hi+lo, pre-packed in the UMMA core-matrix layout by k_pack_mlp) are fetched once per CTA with one
+// cp.async.bulk (TMA) and stay resident; CTAs are persistent over tiles (one CTA per SM).
+#include "fused_common.cuh"
 #include "../../include/psdf_b200.h"
 
-using namespace psdf;
+using namespace psdf_fused;
 
 namespace {
-constexpr int kTile = 128;
-constexpr int kMaxLevels = 32;
-constexpr int kNL = 4;                 // linear layers of the SDF MLP
-constexpr int kATileBytes = 128 * 64 * 2;   // one bf16 operand tile [128 x 64]
-constexpr int kLBO = 128;
-constexpr int kSBO_A = 1024;           // 8 core matrices (K = 64) per 8-row group
-
-struct MlpGeom {
-    int K[kNL], N[kNL];        // true dims
-    int Kp[kNL], Np[kNL];      // padded dims (K % 16 == 0, N % 16 == 0)
-    int w_hi[kNL], w_lo[kNL], bias[kNL];   // byte offsets in the blob
-    int total;
-};
-__host__ __device__ inline int pad16(int v) { return (v + 15) & ~15; }
-inline MlpGeom make_geom(int in_dim, int hidden, int out_dim) {
-    MlpGeom g;
-    int dims[kNL + 1] = {in_dim, hidden, hidden, hidden, out_dim};
-    int off = 0;
-    for (int l = 0; l < kNL; l++) {
-        g.K[l] = dims[l]; g.N[l] = dims[l + 1];
-        g.Kp[l] = pad16(dims[l]); g.Np[l] = pad16(dims[l + 1]);
-        int wbytes = g.Np[l] * g.Kp[l] * 2;
-        g.w_hi[l] = off; off += wbytes;
-        g.w_lo[l] = off; off += wbytes;
-        g.bias[l] = off; off += g.Np[l] * 4;
-    }
-    g.total = (off + 127) & ~127;
-    return g;
-}
-
-// weights [N][K] fp32 (torch.nn.Linear layout) -> hi/lo bf16 in the UMMA K-major core-matrix layout + fp32 bias
-__global__ void k_pack_mlp(MlpGeom g, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
-                           const float* b2, const float* W3, const float* b3, uint8_t* blob) {
-    const float* W[kNL] = {W0, W1, W2, W3};
-    const float* B[kNL] = {b0, b1, b2, b3};
-    int l = blockIdx.y;
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    int total = g.Np[l] * g.Kp[l];
-    if (e < total) {
-        int n = e / g.Kp[l], k = e - n * g.Kp[l];
-        float v = (n < g.N[l] && k < g.K[l]) ? W[l][n * g.K[l] + k] : 0.0f;
-        __nv_bfloat16 hi, lo;
-        umma::split_bf16(v, hi, lo);
-        int sbo = (g.Kp[l] / 8) * kLBO;
-        int off = (n / 8) * sbo + (k / 8) * kLBO + (n % 8) * 16 + (k % 8) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(blob + g.w_hi[l] + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(blob + g.w_lo[l] + off) = lo;
-    }
-    if (e < g.Np[l]) reinterpret_cast<float*>(blob + g.bias[l])[e] = (e < g.N[l]) ? B[l][e] : 0.0f;
-}
-
-// ---------------------------------------------------------------------------------------------- lattice helpers (D = 3)
-struct Simplex3 { int rem0[4]; int rank[4]; float bary[5]; };
-__device__ __forceinline__ void elevate3(const float* cf, float* e) {
-    float sm = 0.0f;
-#pragma unroll
-    for (int i = 3; i > 0; i--) { e[i] = __fmaf_rn(-(float)i, cf[i - 1], sm); sm = __fadd_rn(sm, cf[i - 1]); }
-    e[0] = sm;
-}
-__device__ __forceinline__ void locate3(const float* e, Simplex3& s) {
-    int sum = 0;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float v = __fmul_rn(e[i], 0.25f);
-        float up = __fmul_rn(ceilf(v), 4.0f), down = __fmul_rn(floorf(v), 4.0f);
-        s.rem0[i] = (__fsub_rn(up, e[i]) < __fsub_rn(e[i], down)) ? (int)up : (int)down;
-        sum += s.rem0[i];
-        s.rank[i] = 0;
-    }
-    sum /= 4;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        float di = __fsub_rn(e[i], (float)s.rem0[i]);
-#pragma unroll
-        for (int j = i + 1; j < 4; j++) { if (di < __fsub_rn(e[j], (float)s.rem0[j])) s.rank[i]++; else s.rank[j]++; }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        s.rank[i] += sum;
-        if (s.rank[i] < 0) { s.rank[i] += 4; s.rem0[i] += 4; }
-        else if (s.rank[i] > 3) { s.rank[i] -= 4; s.rem0[i] -= 4; }
-    }
-#pragma unroll
-    for (int i = 0; i < 5; i++) s.bary[i] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float delta = __fmul_rn(__fsub_rn(e[i], (float)s.rem0[i]), 0.25f);
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-            if (r == 3 - s.rank[i]) s.bary[r] = __fadd_rn(s.bary[r], delta);
-            if (r == 4 - s.rank[i]) s.bary[r] = __fsub_rn(s.bary[r], delta);
-        }
-    }
-    s.bary[0] = __fadd_rn(s.bary[0], __fadd_rn(1.0f, s.bary[4]));
-}
-__device__ __forceinline__ unsigned vindex3(const Simplex3& s, int r, unsigned cap_mask, unsigned T) {
-    unsigned h = 0;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        int key = s.rem0[i] + r;
-        if (s.rank[i] > 3 - r) key -= 4;
-        h += (unsigned)key;
-        h *= 2531011u;
-    }
-    return cap_mask ? (h & cap_mask) : (h % T);
-}
-
-__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_d(float z) {
-    float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
-    float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
-    return cdf + z * pdf;
-}
-
-struct FusedParams {
-    int N, L, T;
-    unsigned cap_mask;
-    float points_scaling;
-    int in_dim;          // (L + E) * 2 feature columns
-    MlpGeom g;
-};
-
-struct LevelC { float scale[kMaxLevels * 4]; float shift[kMaxLevels * 4]; float window[kMaxLevels]; };
-
-// store 8 consecutive K values of one row into a hi/lo operand tile pair (one 16-byte core-matrix row each)
-__device__ __forceinline__ void store8(uint8_t* a_hi, uint8_t* a_lo, int row, int kcore, const float* v) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        umma::split_bf16(v[2 * i], h0, l0);
-        umma::split_bf16(v[2 * i + 1], h1, l1);
-        h[i] = umma::pack2(h0, h1);
-        l[i] = umma::pack2(l0, l1);
-    }
-    int off = (row >> 3) * kSBO_A + kcore * kLBO + (row & 7) * 16;
-    *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
-}
-
-__device__ int g_desc_swap = 0;
-
-// issue the three split products of one [128 x Kp] x [Np x Kp]^T GEMM into TMEM (single thread)
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
-                                           const uint8_t* w_lo, int Kp, int Np) {
-    const uint32_t idesc = umma::make_idesc(128, Np, umma::kFmtBF16);
-    const uint32_t sbo_w = (Kp / 8) * kLBO;
-    const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo), wh = umma::smem_u32(w_hi), wl = umma::smem_u32(w_lo);
-    for (int kk = 0; kk < Kp / 16; kk++) {
-        uint32_t ko = kk * 2 * kLBO;      // 16 bf16 = 2 core matrices along K
-        // g_desc_swap: which of the two descriptor offset fields is the K-direction stride (self-test probes this)
-        const bool sw = g_desc_swap != 0;
-        uint64_t dah = sw ? umma::make_desc(ah + ko, kSBO_A, kLBO) : umma::make_desc(ah + ko, kLBO, kSBO_A);
-        uint64_t dal = sw ? umma::make_desc(al + ko, kSBO_A, kLBO) : umma::make_desc(al + ko, kLBO, kSBO_A);
-        uint64_t dwh = sw ? umma::make_desc(wh + ko, sbo_w, kLBO) : umma::make_desc(wh + ko, kLBO, sbo_w);
-        uint64_t dwl = sw ? umma::make_desc(wl + ko, sbo_w, kLBO) : umma::make_desc(wl + ko, kLBO, sbo_w);
-        umma::mma_bf16(tmem_d, dah, dwh, idesc, kk > 0 ? 1u : 0u);
-        umma::mma_bf16(tmem_d, dah, dwl, idesc, 1u);
-        umma::mma_bf16(tmem_d, dal, dwh, idesc, 1u);
-    }
-}
+constexpr int kFusedThreads = 512;
+constexpr int kGroups = kFusedThreads / kTile;
 
 template <bool TAN>
-__global__ void __launch_bounds__(kTile, TAN ? 1 : 2)
+__global__ void __launch_bounds__(kFusedThreads, 1)
 k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restrict__ lattice, const float* __restrict__ scale,
             const float* __restrict__ shift, const float* __restrict__ window, const uint8_t* __restrict__ blob,
             float* __restrict__ sdf_out, float* __restrict__ grad_out, float* __restrict__ geom_out) {
@@ -200,17 +43,18 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
     uint64_t* bars = reinterpret_cast<uint64_t*>(lc + 1);  // [0] weights, [1] mma
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (kTile - 1), grp = tid >> 7;
 
     if (tid == 0) {
         umma::mbar_init(&bars[0], 1);
         umma::mbar_init(&bars[1], 1);
         umma::mbar_fence_init();
     }
-    for (int i = tid; i < P.L * 3; i += kTile) {
+    for (int i = tid; i < P.L * 3; i += kFusedThreads) {
         lc->scale[(i / 3) * 4 + (i % 3)] = scale[i];
         lc->shift[(i / 3) * 4 + (i % 3)] = shift ? shift[i] : 0.0f;
     }
-    for (int i = tid; i < P.L; i += kTile) lc->window[i] = window ? window[i] : 1.0f;
+    for (int i = tid; i < P.L; i += kFusedThreads) lc->window[i] = window ? window[i] : 1.0f;
     __syncthreads();
     if (warp == 0) umma::tmem_alloc(tmem_slot, S * 64);
     if (tid == 0) {
@@ -223,23 +67,24 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
     const uint32_t tmem_base = *tmem_slot;
     umma::mbar_wait(&bars[0], 0);
     uint32_t mma_phase = 0;
+    const int level_cores = P.L / 4;                        // 4 levels x 2 features = one 16-byte core row
+    const int all_cores = P.g.Kp[0] / 8;
 
     const int ntiles = (P.N + kTile - 1) / kTile;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int n = tile * kTile + tid;
+        const int n = tile * kTile + row;
         const bool valid = n < P.N;
         float x[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) x[i] = valid ? pos[(size_t)n * 3 + i] : 0.0f;
 
-        // ---------------- encoder: 4 levels (= 8 feature columns = one 16-byte core row) at a time
-        for (int l0 = 0; l0 < P.L; l0 += 4) {
+        // ---------------- encoder: operand cores grp, grp+4, ... of this row
+        for (int kc = grp; kc < all_cores; kc += kGroups) {
             float fv[8], ft[3][8];
+            if (kc < level_cores) {
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int l = l0 + q;
-                float a0 = 0.f, a1 = 0.f, t0[3] = {0.f, 0.f, 0.f}, t1[3] = {0.f, 0.f, 0.f};
-                if (l < P.L) {
+                for (int q = 0; q < 4; q++) {
+                    const int l = kc * 4 + q;
                     float cf[3], e[4];
 #pragma unroll
                     for (int i = 0; i < 3; i++) cf[i] = __fmul_rn(__fadd_rn(x[i], lc->shift[l * 4 + i]), lc->scale[l * 4 + i]);
@@ -251,17 +96,20 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
 #pragma unroll
                     for (int r = 0; r < 4; r++) v[r] = __ldg(tab + vindex3(s, r, P.cap_mask, (unsigned)P.T));
                     const float w = lc->window[l];
+                    float a0 = 0.f, a1 = 0.f;
 #pragma unroll
                     for (int r = 0; r < 4; r++) { float wr = s.bary[r] * w; a0 = fmaf(v[r].x, wr, a0); a1 = fmaf(v[r].y, wr, a1); }
+                    fv[2 * q] = a0; fv[2 * q + 1] = a1;
                     if (TAN) {
 #pragma unroll
                         for (int j = 0; j < 3; j++) {
                             // tangent of the weights along e_j: same rank scatter applied to the elevated direction
-                            float dcf[3] = {0.f, 0.f, 0.f};
-                            dcf[j] = lc->scale[l * 4 + j];
                             float de[4], sm = 0.f;
 #pragma unroll
-                            for (int i = 3; i > 0; i--) { de[i] = sm - (float)i * dcf[i - 1]; sm += dcf[i - 1]; }
+                            for (int i = 3; i > 0; i--) {
+                                float dc = (i - 1 == j) ? lc->scale[l * 4 + j] : 0.f;
+                                de[i] = sm - (float)i * dc; sm += dc;
+                            }
                             de[0] = sm;
                             float db[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -271,43 +119,33 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
                                 for (int r = 0; r < 5; r++) { if (r == 3 - s.rank[i]) db[r] += dl; if (r == 4 - s.rank[i]) db[r] -= dl; }
                             }
                             db[0] += db[4];
+                            float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-                            for (int r = 0; r < 4; r++) { float c = db[r] * w; t0[j] = fmaf(v[r].x, c, t0[j]); t1[j] = fmaf(v[r].y, c, t1[j]); }
+                            for (int r = 0; r < 4; r++) { float c = db[r] * w; t0 = fmaf(v[r].x, c, t0); t1 = fmaf(v[r].y, c, t1); }
+                            ft[j][2 * q] = t0; ft[j][2 * q + 1] = t1;
                         }
                     }
                 }
-                fv[2 * q] = a0; fv[2 * q + 1] = a1;
-                if (TAN) {
-#pragma unroll
-                    for (int j = 0; j < 3; j++) { ft[j][2 * q] = t0[j]; ft[j][2 * q + 1] = t1[j]; }
-                }
-            }
-            store8(s_a, s_a + kATileBytes, tid, l0 / 4, fv);
-            if (TAN) {
-#pragma unroll
-                for (int j = 0; j < 3; j++) store8(s_a + (1 + j) * 2 * kATileBytes, s_a + (1 + j) * 2 * kATileBytes + kATileBytes, tid, l0 / 4, ft[j]);
-            }
-        }
-        // concat-points columns and zero padding up to Kp[0] (columns 2L .. Kp0-1)
-        {
-            const int c0 = 2 * P.L;                 // first concat column, multiple of 8 when L % 4 == 0
-            for (int kc = c0 / 8; kc < P.g.Kp[0] / 8; kc++) {
-                float fv[8], ft[3][8];
+            } else {
+                // concat-points columns (x * scaling) and zero padding up to Kp[0]
+                const int c0 = 2 * P.L;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
-                    int c = kc * 8 + i - c0;        // concat index
+                    int c = kc * 8 + i - c0;
                     float val = 0.f;
 #pragma unroll
                     for (int d = 0; d < 3; d++) if (c == d && (c0 + c) < P.in_dim) val = x[d] * P.points_scaling;
                     fv[i] = val;
+                    if (TAN) {
 #pragma unroll
-                    for (int j = 0; j < 3; j++) ft[j][i] = (c == j && (c0 + c) < P.in_dim) ? P.points_scaling : 0.f;
+                        for (int j = 0; j < 3; j++) ft[j][i] = (c == j && (c0 + c) < P.in_dim) ? P.points_scaling : 0.f;
+                    }
                 }
-                store8(s_a, s_a + kATileBytes, tid, kc, fv);
-                if (TAN) {
+            }
+            store8(s_a, s_a + kATileBytes, row, kc, fv);
+            if (TAN) {
 #pragma unroll
-                    for (int j = 0; j < 3; j++) store8(s_a + (1 + j) * 2 * kATileBytes, s_a + (1 + j) * 2 * kATileBytes + kATileBytes, tid, kc, ft[j]);
-                }
+                for (int j = 0; j < 3; j++) store8(s_a + (1 + j) * 2 * kATileBytes, s_a + (1 + j) * 2 * kATileBytes + kATileBytes, row, kc, ft[j]);
             }
         }
 
@@ -328,9 +166,10 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
             mma_phase ^= 1;
             umma::fence_after_sync();
             const float* bias = reinterpret_cast<const float*>(s_blob + P.g.bias[l]);
-            const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+            const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
             const bool last = (l == kNL - 1);
-            for (int c = 0; c < P.g.Np[l] / 16; c++) {
+            const int c = grp;                                  // this thread's 16-column chunk
+            if (c < P.g.Np[l] / 16) {
                 float z[16], tz[3][16];
                 umma::tmem_ld16(trow + c * 16, z);
                 if (TAN) {
@@ -341,24 +180,23 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
 #pragma unroll
                 for (int i = 0; i < 16; i++) z[i] += bias[c * 16 + i];
                 if (!last) {
-                    float a[16];
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
-                        a[i] = gelu_f(z[i]);
                         if (TAN) {
                             float g1 = gelu_d(z[i]);
 #pragma unroll
                             for (int j = 0; j < 3; j++) tz[j][i] *= g1;
                         }
+                        z[i] = gelu_f(z[i]);
                     }
-                    store8(s_a, s_a + kATileBytes, tid, 2 * c, a);
-                    store8(s_a, s_a + kATileBytes, tid, 2 * c + 1, a + 8);
+                    store8(s_a, s_a + kATileBytes, row, 2 * c, z);
+                    store8(s_a, s_a + kATileBytes, row, 2 * c + 1, z + 8);
                     if (TAN) {
 #pragma unroll
                         for (int j = 0; j < 3; j++) {
                             uint8_t* hi = s_a + (1 + j) * 2 * kATileBytes;
-                            store8(hi, hi + kATileBytes, tid, 2 * c, tz[j]);
-                            store8(hi, hi + kATileBytes, tid, 2 * c + 1, tz[j] + 8);
+                            store8(hi, hi + kATileBytes, row, 2 * c, tz[j]);
+                            store8(hi, hi + kATileBytes, row, 2 * c + 1, tz[j] + 8);
                         }
                     }
                 } else if (valid) {
@@ -444,7 +282,10 @@ __global__ void __launch_bounds__(kTile) k_debug_gemm(int N, int K, const float*
 
 extern "C" {
 
-long long psdf_sdf_mlp_blob_bytes(int in_dim, int hidden, int out_dim) { return make_geom(in_dim, hidden, out_dim).total; }
+long long psdf_sdf_mlp_blob_bytes(int in_dim, int hidden, int out_dim) {
+    MlpGeom g = make_geom(in_dim, hidden, out_dim);
+    return (long long)g.total + g.total_t;     // forward operands + transposed copy for the backward
+}
 
 int psdf_sdf_mlp_pack(int in_dim, int hidden, int out_dim, const float* W0, const float* b0, const float* W1, const float* b1,
                       const float* W2, const float* b2, const float* W3, const float* b3, uint8_t* blob, void* stream) {
@@ -477,19 +318,15 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
         size_t smem = (size_t)P.g.total + 4 * 2 * kATileBytes + sizeof(LevelC) + 64;
         static bool attr_done = false;
         if (!attr_done) { cudaFuncSetAttribute(k_sdf_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_done = true; }
-        k_sdf_fused<true><<<min(ntiles, sms), kTile, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
+        k_sdf_fused<true><<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
     } else {
         size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + 64;
         static bool attr_done = false;
         if (!attr_done) { cudaFuncSetAttribute(k_sdf_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); attr_done = true; }
-        k_sdf_fused<false><<<min(ntiles, 2 * sms), kTile, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
+        k_sdf_fused<false><<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
     }
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
-}
-
-int psdf_debug_set_desc_swap(int swap) {
-    return cudaMemcpyToSymbol(g_desc_swap, &swap, sizeof(int)) == cudaSuccess ? PSDF_OK : PSDF_ERR_LAUNCH;
 }
 
 int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream) {

@@ -650,7 +650,15 @@ k_random_rays_from_reel(int nr_rays, int H, int W, const float* __restrict__ rgb
     gt_mask[i] = m;
 }
 
-inline GridGeom geom(int V, float extent, const float* t) { GridGeom g; g.V = V; g.extent = extent; g.tx = t[0]; g.ty = t[1]; g.tz = t[2]; return g; }
+inline GridGeom geom(int V, float extent, const float* t) {
+    GridGeom g;
+    g.V = V; g.extent = extent; g.tx = t[0]; g.ty = t[1]; g.tz = t[2];
+    int ex = 0;
+    float m = frexpf(extent, &ex);
+    g.inv_extent = (m == 0.5f) ? 1.0f / extent : 0.0f;      // exact reciprocal only for powers of two
+    g.inv_V = 1.0f / (float)V;
+    return g;
+}
 #define ST ((cudaStream_t)stream)
 }  // namespace
 

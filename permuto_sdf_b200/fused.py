@@ -41,6 +41,20 @@ class FusedSDF:
              l[1].bias.detach(), l[2].weight.detach(), l[2].bias.detach(), l[3].weight.detach(), l[3].bias.detach(), self.blob)
         self._versions = self._cur_versions()
 
+    # ------------------------------------------------------------------------------------------ training path
+    def train_forward(self, points, iter_nr):
+        """differentiable (wrt lattice + MLP parameters) sdf, d sdf/dx, geom in two fused kernels (forward, backward).
+        Equivalent to SDF.get_sdf_and_gradient(points, iter_nr) followed by loss.backward() through its double backward;
+        the gradient wrt `points` is not produced (it only matters for the 1e-4-scaled shift of the curvature loss)."""
+        if self._versions != self._cur_versions():
+            self.repack()
+        m = self.model
+        m.last_iter_nr = iter_nr
+        window = m.window(iter_nr).view(-1).contiguous()
+        l = self.lin
+        return _FusedSDFTrainFn.apply(points.detach().contiguous(), m.encoding.lattice_values, l[0].weight, l[0].bias, l[1].weight, l[1].bias,
+                                      l[2].weight, l[2].bias, l[3].weight, l[3].bias, window, self)
+
     @torch.no_grad()
     def __call__(self, points, iter_nr, with_gradient=False, with_geom=True):
         """-> (sdf [N,1], gradient [N,3] or None, geom_feat [N,out-1] or None)"""
@@ -58,3 +72,46 @@ class FusedSDF:
         call("psdf_sdf_fused_forward", N, enc.nr_levels, enc.capacity, pts, enc.lattice_values.detach(), enc.scale_factor,
              enc.shift_tensor(), window, enc.concat_points_scaling, self.hidden, self.out_dim, self.blob, sdf, grad, geom)
         return sdf, grad, geom
+
+
+def _pad16(v):
+    return (v + 15) // 16 * 16
+
+
+class _FusedSDFTrainFn(torch.autograd.Function):
+    """forward: psdf_sdf_fused_forward (value + 3 tangent streams); backward: psdf_sdf_fused_backward (value + the tangent
+    along the upstream gradient, reverse sweep on the tensor cores, lattice scatter fused) + 4 library GEMMs for dW."""
+
+    @staticmethod
+    def forward(ctx, points, lattice, W0, b0, W1, b1, W2, b2, W3, b3, window, fused):
+        enc = fused.model.encoding
+        N = points.shape[0]
+        dev = points.device
+        sdf = torch.empty(N, 1, device=dev)
+        grad = torch.empty(N, 3, device=dev)
+        geom = torch.empty(N, fused.out_dim - 1, device=dev)
+        call("psdf_sdf_fused_forward", N, enc.nr_levels, enc.capacity, points, lattice.detach(), enc.scale_factor, enc.shift_tensor(), window,
+             enc.concat_points_scaling, fused.hidden, fused.out_dim, fused.blob, sdf, grad, geom)
+        ctx.fused = fused
+        ctx.save_for_backward(points, lattice, window)
+        return sdf, grad, geom
+
+    @staticmethod
+    def backward(ctx, g_sdf, g_grad, g_geom):
+        fused = ctx.fused
+        points, lattice, window = ctx.saved_tensors
+        enc = fused.model.encoding
+        N = points.shape[0]
+        dev = points.device
+        dims_k = [fused.in_dim, fused.hidden, fused.hidden, fused.hidden]
+        dims_n = [fused.hidden, fused.hidden, fused.hidden, fused.out_dim]
+        zcat = [torch.empty(2 * N, _pad16(n), device=dev) for n in dims_n]
+        acat = [torch.empty(2 * N, _pad16(k), device=dev) for k in dims_k]
+        gb = [torch.zeros(n, device=dev) for n in dims_n]
+        g_lat = torch.zeros_like(lattice)
+        c = lambda t: None if t is None else t.contiguous()
+        call("psdf_sdf_fused_backward", N, enc.nr_levels, enc.capacity, points, lattice.detach(), enc.scale_factor, enc.shift_tensor(), window,
+             enc.concat_points_scaling, fused.hidden, fused.out_dim, fused.blob, c(g_sdf), c(g_grad), c(g_geom), g_lat, zcat[0], zcat[1], zcat[2],
+             zcat[3], acat[0], acat[1], acat[2], acat[3], gb[0], gb[1], gb[2], gb[3])
+        gW = [(zcat[l].t() @ acat[l])[:dims_n[l], :dims_k[l]] for l in range(4)]     # plain library GEMMs [Np, 2N] x [2N, Kp]
+        return (None, g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)

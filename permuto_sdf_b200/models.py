@@ -123,6 +123,12 @@ class SDF(torch.nn.Module):
         self.fused = FusedSDF(self)
         return self.fused
 
+    def enable_fused_training(self, flag=True):
+        """get_sdf_and_gradient (autograd mode) through the fused forward/backward kernels"""
+        if getattr(self, "fused", None) is None:
+            self.enable_fused_inference()
+        self.fused_training = bool(flag)
+
     def forward(self, points, iter_nr):
         assert points.shape[1] == self.in_channels, "points should be N x in_channels"
         self.last_iter_nr = iter_nr
@@ -148,6 +154,9 @@ class SDF(torch.nn.Module):
             s = sdf_full.chunk(4, dim=0)
             grads = torch.cat([(s[1] - s[0]) / eps, (s[2] - s[0]) / eps, (s[3] - s[0]) / eps], 1)
             return s[0], grads, geom
+        if getattr(self, "fused_training", False) and getattr(self, "fused", None) is not None and torch.is_grad_enabled():
+            # one fused forward kernel (+ one fused backward kernel when loss.backward() runs), csrc/fused_sdf*.cu
+            return self.fused.train_forward(points, iter_nr)
         with torch.set_grad_enabled(True):
             points.requires_grad_(True)
             sdf, geom = self.forward(points, iter_nr)

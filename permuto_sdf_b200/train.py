@@ -213,7 +213,7 @@ class Trainer:
     per-iteration step of train_permuto_sdf.py:311-422 (after sphere init), with `--with_mask` semantics."""
 
     def __init__(self, hyperparams=None, nr_levels=24, capacity=2 ** 18, sdf_hidden=32, nr_images=8, occupancy_resolution=256,
-                 seed=0, with_colorcal=True, optimizer="adamw", fused_inference=True):
+                 seed=0, with_colorcal=True, optimizer="adamw", fused_inference=True, fused_training=True):
         torch.manual_seed(seed)
         self._fused_inference = fused_inference
         self.hp = hyperparams or HyperParams()
@@ -226,6 +226,8 @@ class Trainer:
         self.occupancy_grid = OccupancyGrid(occupancy_resolution, 1.0, [0, 0, 0]) if hp.use_occupancy_grid else None
         if fused_inference and nr_levels % 4 == 0 and sdf_hidden % 16 == 0 and sdf_hidden <= 64 and self.model_sdf.encoding.output_dims() <= 64:
             self.model_sdf.enable_fused_inference()
+            if fused_training:
+                self.model_sdf.enable_fused_training()
         groups = [{"params": list(self.model_sdf.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_sdf"}]
         if self.model_bg is not None:
             groups.append({"params": list(self.model_bg.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_bg"})

@@ -26,18 +26,6 @@ def _gemm_err(N, K):
     return rel(D, A.double() @ B.double().t())
 
 
-def test_descriptor_convention_probe(cuda):
-    """the library default must be the working convention; the probe prints what the other one gives"""
-    from permuto_sdf_b200 import load_library
-    lib = load_library()
-    errs = {}
-    for sw in (1, 0):
-        assert lib.psdf_debug_set_desc_swap(sw) == 0
-        errs[sw] = _gemm_err(64, 64)
-    print("umma descriptor probe: rel err with LBO=K-stride (default): %g, swapped: %g" % (errs[0], errs[1]))
-    assert errs[0] < 5e-5, "default descriptor convention is wrong: %s" % errs
-
-
 @pytest.mark.parametrize("N,K", [(64, 64), (48, 64), (64, 48), (16, 16), (33, 36)])
 def test_umma_gemm_self_test(cuda, N, K):
     from permuto_sdf_b200 import call
@@ -84,6 +72,44 @@ def test_fused_sdf_matches_oracle_and_model(cuda, L, hidden, N):
         lin[3].bias += 0.25
     s2, _, _ = f(pos.cuda(), it)
     assert rel(s2, s0 + 0.25) < 1e-3
+
+
+@pytest.mark.parametrize("L,hidden,N", [(16, 64, 3000), (8, 32, 500), (24, 32, 129), (16, 64, 65536)])
+def test_fused_training_gradients_match_autograd(cuda, L, hidden, N):
+    """parameter gradients of a loss on (sdf, d sdf/dx, geom): fused forward+backward kernels vs autograd through the
+    modular path (encoding double backward + torch MLP). North-star tolerance 1e-3 relative."""
+    from permuto_sdf import Sphere
+    from permuto_sdf_b200.models import SDF
+    torch.manual_seed(L + N)
+    m = SDF(3, Sphere(0.5, [0, 0, 0]), 32, 10000, nr_levels=L, capacity=2 ** 16, hidden=hidden).to("cuda")
+    with torch.no_grad():
+        m.encoding.lattice_values.normal_(0, 0.3)
+    pos = ((torch.rand(N, 3, device="cuda") - 0.5) * 0.9)
+    tgt = torch.randn(N, 3, device="cuda")
+    wgeom = torch.randn(32, device="cuda")
+
+    def loss_fn(sdf, grad, geom):
+        return ((grad.norm(dim=-1) - 1.0) ** 2).mean() + (sdf ** 2).mean() + (grad * tgt).sum(-1).mean() + (torch.tanh(geom) * wgeom).mean()
+
+    params = [m.encoding.lattice_values] + [p for l in m.mlp_sdf if isinstance(l, torch.nn.Linear) for p in (l.weight, l.bias)]
+    it = 4000
+    sdf0, grad0, geom0 = m.get_sdf_and_gradient(pos.clone(), it)
+    l0 = loss_fn(sdf0, grad0, geom0)
+    g0 = torch.autograd.grad(l0, params)
+    m.enable_fused_training()
+    assert m.fused_training
+    sdf1, grad1, geom1 = m.get_sdf_and_gradient(pos.clone(), it)
+    l1 = loss_fn(sdf1, grad1, geom1)
+    g1 = torch.autograd.grad(l1, params)
+    assert rel(sdf1, sdf0) < 1e-3 and rel(grad1, grad0) < 1e-3 and rel(geom1, geom0) < 1e-3
+    assert abs(float(l1) - float(l0)) < 1e-3 * abs(float(l0))
+    names = ["lattice", "W0", "b0", "W1", "b1", "W2", "b2", "W3", "b3"]
+    errs = {n: rel(a, b) for n, a, b in zip(names, g1, g0)}
+    assert max(errs.values()) < 1e-3, errs
+    # a second call accumulates into .grad like any autograd op
+    m.zero_grad()
+    loss_fn(*m.get_sdf_and_gradient(pos.clone(), it)).backward()
+    assert rel(m.encoding.lattice_values.grad, g0[0]) < 1e-3
 
 
 def test_fused_sdf_large_and_ragged(cuda):
