@@ -121,27 +121,10 @@ def central_pixels(n, H, W, box, gen):
     return (y * W + x).to(torch.int32)
 
 
-class FlatGrads:
-    """all parameter gradients as views into one flat buffer -> a single NCCL all-reduce per step"""
-
-    def __init__(self, params):
-        self.params = [p for p in params if p.requires_grad]
-        n = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(n, device=self.params[0].device)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
-
-    def allreduce_mean(self, world):
-        import torch.distributed as dist
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-        self.flat.mul_(1.0 / world)
-
-
 def run_ours(args):
     import torch.distributed as dist
     from permuto_sdf_b200 import _lib, load_library
+    from permuto_sdf_b200.dist import FlatGrads
     from permuto_sdf_b200.permuto_sdf import PermutoSDF
     from permuto_sdf_b200.train import HyperParams, Trainer
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -161,12 +144,14 @@ def run_ours(args):
     hp.nr_samples_imp_sampling = 16
     hp.nr_rays = NR_RAYS
     tr = Trainer(hp, nr_levels=16, capacity=2 ** 18, sdf_hidden=64, nr_images=8, occupancy_resolution=256, seed=0,
-                 fused_inference=not args.modular, fused_training=not args.modular)
+                 fused_inference=not args.modular, fused_training=not args.modular, optimizer="adamw" if args.modular else "fused")
     tr.set_analytic_scene()
     tr.iter_nr = 20000          # past coarse-to-fine: all 16 levels active, cos-anneal half way
     H, W, f = 600, 800, 1000.0
     reel = analytic_reel(8, H, W, f, dev)
-    flat = FlatGrads(tr.params) if world > 1 else None
+    flat = None
+    if world > 1 and not hasattr(tr.optimizer, "flat_grad"):
+        flat = FlatGrads(tr.params)
 
     total = args.steps + args.warmup
     gen = torch.Generator().manual_seed(1000 + rank)
@@ -183,10 +168,11 @@ def run_ours(args):
             pix, img = pix_dev[i], img_dev[i]
         with torch.no_grad():
             o, d, gt, gm, img_idx = PermutoSDF.rays_from_reel_indices(reel, pix, img)
-        loss = tr.step(o, d, gt, gm, img_idx, update_occupancy=(i % 8 == 0), optimizer_step=(flat is None))
-        if flat is not None:
-            flat.allreduce_mean(world)
-            tr.optimizer.step()
+        loss = tr.step(o, d, gt, gm, img_idx, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1))
+        if world > 1:
+            # the single collective of the path: one NCCL all-reduce of the flat gradient buffer, mean folded into AdamW
+            dist.all_reduce(tr.optimizer.flat_grad if flat is None else flat.flat, op=dist.ReduceOp.SUM)
+            tr.optimizer_step(grad_scale=1.0 / world)
         if e2e:
             return float(loss)          # device -> host read of the step's result
         return loss

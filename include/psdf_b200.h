@@ -180,6 +180,12 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
                             const float* g_grad, const float* g_geom, float* grad_lattice, float* zcat0, float* zcat1, float* zcat2,
                             float* zcat3, float* acat0, float* acat1, float* acat2, float* acat3, float* gb0, float* gb1, float* gb2,
                             float* gb3, void* stream);
+/* ---------------------------------------------------------------- dense fused AdamW (torch.optim.AdamW / apex FusedAdam math,
+ * train_permuto_sdf.py:293-304); step >= 1 is the incremented step count; grad is multiplied by grad_scale and, when
+ * zero_grad != 0, reset to zero in the same pass. Pointers 16-byte aligned. */
+int psdf_adamw_step(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, int zero_grad, void* stream);
+
 /* self-test of the tensor-core path: D[128,N] = A[128,K] * B[N,K]^T (N,K <= 64) */
 int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream);
 

@@ -1,0 +1,75 @@
+// Dense fused AdamW sweep for the hash tables and MLP parameters (sm_100a).
+// One pass over {param, grad, exp_avg, exp_avg_sq}: 28 B/parameter (read 16, write 12), optional gradient
+// zeroing folded in (+4 B) so that no separate zero_grad memset is needed. Math = torch.optim.AdamW /
+// apex FusedAdam as used by the reference (train_permuto_sdf.py:293-304: betas (0.9, 0.99), eps 1e-15,
+// decoupled weight decay, no amsgrad):
+//   p  <- p (1 - lr wd);  m <- b1 m + (1-b1) g;  v <- b2 v + (1-b2) g^2
+//   p  <- p - lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// HBM-bound streaming kernel: 128-bit loads/stores, grid = multiple of the SM count, grid-stride loop.
+#include "common.cuh"
+#include "../../include/psdf_b200.h"
+
+using namespace psdf;
+
+namespace {
+__global__ void __launch_bounds__(256)
+k_adamw(long long n, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float lr,
+        float beta1, float beta2, float eps, float weight_decay, float bias_c1, float bias_c2_sqrt, float grad_scale, int zero_grad) {
+    const long long n4 = n >> 2;
+    const float decay = 1.0f - lr * weight_decay;
+    const float step_size = lr / bias_c1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i];
+        float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
+        float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float gr = gg[k] * grad_scale;
+            float pk = pp[k] * decay;
+            mm[k] = beta1 * mm[k] + (1.0f - beta1) * gr;
+            vv[k] = beta2 * vv[k] + (1.0f - beta2) * gr * gr;
+            float denom = sqrtf(vv[k]) / bias_c2_sqrt + eps;
+            pp[k] = pk - step_size * (mm[k] / denom);
+        }
+        reinterpret_cast<float4*>(p)[i] = P;
+        reinterpret_cast<float4*>(m)[i] = M;
+        reinterpret_cast<float4*>(v)[i] = V;
+        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // tail
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        long long i = (n4 << 2) + threadIdx.x;
+        float gr = g[i] * grad_scale;
+        float pk = p[i] * decay;
+        float mk = beta1 * m[i] + (1.0f - beta1) * gr;
+        float vk = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+        m[i] = mk; v[i] = vk;
+        p[i] = pk - step_size * (mk / (sqrtf(vk) / bias_c2_sqrt + eps));
+        if (zero_grad) g[i] = 0.f;
+    }
+}
+#define ST ((cudaStream_t)stream)
+}  // namespace
+
+extern "C" {
+// step >= 1 is the (already incremented) step count; pointers must be 16-byte aligned
+int psdf_adamw_step(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, float grad_scale, int zero_grad, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    if (step < 1) return PSDF_ERR_ARG;
+    if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0) return PSDF_ERR_ARG;
+    double c1 = 1.0 - pow((double)beta1, (double)step);
+    double c2 = 1.0 - pow((double)beta2, (double)step);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long n4 = n >> 2;
+    int blocks = (int)((n4 + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    if (blocks > sms * 8) blocks = sms * 8;
+    k_adamw<<<blocks, 256, 0, ST>>>(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, (float)c1, (float)sqrt(c2),
+                                   grad_scale, zero_grad);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+}  // extern "C"

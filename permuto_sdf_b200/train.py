@@ -237,7 +237,11 @@ class Trainer:
         if self.model_colorcal is not None:
             groups.append({"params": list(self.model_colorcal.parameters()), "weight_decay": 1e-1, "lr": hp.lr, "name": "model_colorcal"})
         self.params = [p for g in groups for p in g["params"]]
-        self.optimizer = torch.optim.AdamW(groups, amsgrad=False, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, lr=hp.lr)
+        if optimizer == "fused":
+            from .optim import FusedAdamW      # our dense AdamW kernel over flat buffers (csrc/optim.cu)
+            self.optimizer = FusedAdamW(groups, betas=(0.9, 0.99), eps=1e-15, lr=hp.lr)
+        else:
+            self.optimizer = torch.optim.AdamW(groups, amsgrad=False, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, lr=hp.lr)
         self.iter_nr = 0
         self.nr_rays_to_create = hp.nr_rays
         self.last = {}
@@ -301,6 +305,18 @@ class Trainer:
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
         if optimizer_step:
-            self.optimizer.step()
+            self.optimizer_step()
         self.iter_nr += 1
         return loss.detach()
+
+    def optimizer_step(self, grad_scale=1.0):
+        if hasattr(self.optimizer, "flat_grad"):
+            self.optimizer.step(grad_scale=grad_scale)
+            if getattr(self.model_sdf, "fused", None) is not None:
+                self.model_sdf.fused.repack()      # raw-pointer updates do not bump tensor versions
+        else:
+            if grad_scale != 1.0:
+                for p in self.params:
+                    if p.grad is not None:
+                        p.grad.mul_(grad_scale)
+            self.optimizer.step()
