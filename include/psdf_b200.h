@@ -135,6 +135,25 @@ int psdf_vr_volume_render_nerf_backward(PSDF_RSP, const float* grad_pred_rgb, co
                                         const float* radiance, const float* samples_dt, float* grad_rgb, float* grad_radiance,
                                         void* stream);
 
+/* Fused NeuS compositing + per-ray losses (training): replaces VolumeRenderingNeus.compute_weights + integrate
+ * (permuto_sdf_py/volume_rendering/volume_rendering_modules.py:129-176) and the rgb / mask / eikonal losses
+ * (permuto_sdf_py/train_permuto_sdf.py:349-383, permuto_sdf_py/utils/permuto_sdf_utils.py:43-51) in one launch each way.
+ * sdf [N], grad/rgb/dirs [N,3], dt [N], inv_s_dev [1] (device scalar, clipped to [1e-6,1e6] inside), gt_rgb [R,3],
+ * gt_mask [R] or NULL, hit [R] u8 or NULL, bg_rgb [R,3] or NULL (pred += bg_T * bg_rgb).
+ * ray_loss [R,3] = {sum_c |gt-pred| * hit, BCE(clip(w_sum,1e-3,1-1e-3), mask), sum_i (|grad_i|-1)^2}. */
+int psdf_neus_render_loss_forward(PSDF_RSP, const float* sdf, const float* grad, const float* rgb, const float* dirs, const float* dt,
+                                  const float* inv_s_dev, float cos_anneal_ratio, const float* gt_rgb, const float* gt_mask,
+                                  const uint8_t* hit, const float* bg_rgb, float* alpha, float* transmittance, float* weights,
+                                  float* pred_rgb, float* weights_sum, float* bg_transmittance, float* ray_loss, void* stream);
+/* d loss / d {sdf, grad, rgb, bg_rgb, inv_s} for loss = g_total * (scale_rgb * sum rgb-term + scale_mask * sum bce + scale_eik * sum eik);
+ * g_total_dev [1] device scalar or NULL (=1); g_bg_rgb / g_inv_s may be NULL; g_inv_s is accumulated (+=). */
+int psdf_neus_render_loss_backward(PSDF_RSP, const float* sdf, const float* grad, const float* rgb, const float* dirs, const float* dt,
+                                   const float* inv_s_dev, float cos_anneal_ratio, const float* gt_rgb, const float* gt_mask,
+                                   const uint8_t* hit, const float* bg_rgb, const float* alpha, const float* transmittance,
+                                   const float* pred_rgb, const float* weights_sum, const float* bg_transmittance,
+                                   const float* g_total_dev, float scale_rgb, float scale_mask, float scale_eik, float* g_sdf,
+                                   float* g_grad, float* g_rgb, float* g_bg_rgb, float* g_inv_s, void* stream);
+
 /* ---------------------------------------------------------------- PermutoSDF statics (include/permuto_sdf/PermutoSDF.cuh:46-55) */
 int psdf_spherical_harmonics(int n, int degree, const float* dirs, float* out, void* stream);
 int psdf_random_rays_from_reel(int nr_rays, int nr_images, int H, int W, const float* rgb_reel, const float* mask_reel,

@@ -82,6 +82,11 @@ __device__ __forceinline__ void elevate3(const float* cf, float* e) {
     for (int i = 3; i > 0; i--) { e[i] = __fmaf_rn(-(float)i, cf[i - 1], sm); sm = __fadd_rn(sm, cf[i - 1]); }
     e[0] = sm;
 }
+// D[k] = d[i] of the coordinate i whose rank is k (ranks are a permutation of 0..3)
+__device__ __forceinline__ void by_rank(const Simplex3& s, const float* d, float* D) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) D[k] = s.rank[0] == k ? d[0] : (s.rank[1] == k ? d[1] : (s.rank[2] == k ? d[2] : d[3]));
+}
 __device__ __forceinline__ void locate3(const float* e, Simplex3& s) {
     int sum = 0;
 #pragma unroll
@@ -105,18 +110,26 @@ __device__ __forceinline__ void locate3(const float* e, Simplex3& s) {
         if (s.rank[i] < 0) { s.rank[i] += 4; s.rem0[i] += 4; }
         else if (s.rank[i] > 3) { s.rank[i] -= 4; s.rem0[i] -= 4; }
     }
+    // barycentric weights: with D_k the fractional offset of the coordinate of rank k, the reference's scatter
+    // (+delta at 3 - rank, -delta at 4 - rank) is bary_r = D_{3-r} - D_{4-r}, bary_0 = D_3 + (1 - D_0)
+    float delta[4], D[4];
 #pragma unroll
-    for (int i = 0; i < 5; i++) s.bary[i] = 0.0f;
+    for (int i = 0; i < 4; i++) delta[i] = __fmul_rn(__fsub_rn(e[i], (float)s.rem0[i]), 0.25f);
+    by_rank(s, delta, D);
+    s.bary[0] = __fadd_rn(D[3], __fsub_rn(1.0f, D[0]));
+    s.bary[1] = __fsub_rn(D[2], D[3]);
+    s.bary[2] = __fsub_rn(D[1], D[2]);
+    s.bary[3] = __fsub_rn(D[0], D[1]);
+    s.bary[4] = -D[0];
+}
+// tangent of the barycentric weights along the (scaled) direction dcf: the same rank scatter applied to its elevation
+__device__ __forceinline__ void bary_tangent3(const float* dcf, const Simplex3& s, float* db) {
+    float de[4], dD[4], sm = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float delta = __fmul_rn(__fsub_rn(e[i], (float)s.rem0[i]), 0.25f);
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-            if (r == 3 - s.rank[i]) s.bary[r] = __fadd_rn(s.bary[r], delta);
-            if (r == 4 - s.rank[i]) s.bary[r] = __fsub_rn(s.bary[r], delta);
-        }
-    }
-    s.bary[0] = __fadd_rn(s.bary[0], __fadd_rn(1.0f, s.bary[4]));
+    for (int i = 3; i > 0; i--) { de[i] = (sm - (float)i * dcf[i - 1]) * 0.25f; sm += dcf[i - 1]; }
+    de[0] = sm * 0.25f;
+    by_rank(s, de, dD);
+    db[0] = dD[3] - dD[0]; db[1] = dD[2] - dD[3]; db[2] = dD[1] - dD[2]; db[3] = dD[0] - dD[1];
 }
 __device__ __forceinline__ unsigned vindex3(const Simplex3& s, int r, unsigned cap_mask, unsigned T) {
     unsigned h = 0;
@@ -130,12 +143,22 @@ __device__ __forceinline__ unsigned vindex3(const Simplex3& s, int r, unsigned c
     return cap_mask ? (h & cap_mask) : (h % T);
 }
 
-__device__ __forceinline__ float gelu_f(float z) { return 0.5f * z * (1.0f + erff(z * 0.70710678118654752f)); }
-__device__ __forceinline__ float gelu_d(float z) {
-    float cdf = 0.5f * (1.0f + erff(z * 0.70710678118654752f));
-    float pdf = 0.3989422804014327f * __expf(-0.5f * z * z);
-    return cdf + z * pdf;
+// exact (erf) GELU and derivatives from one exp and one reciprocal: Phi(z) by Abramowitz-Stegun 7.1.26 (|err| < 1e-7),
+// whose e^{-x^2} factor at x = z / sqrt(2) is the Gaussian that the derivative needs anyway.
+struct GeluEval { float cdf, pdf; };
+__device__ __forceinline__ GeluEval gelu_eval(float z) {
+    GeluEval o;
+    float E = __expf(-0.5f * z * z);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752f, fabsf(z), 1.0f)));
+    float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+    float q = 0.5f * poly * E;
+    o.cdf = z >= 0.f ? 1.0f - q : q;
+    o.pdf = 0.3989422804014327f * E;
+    return o;
 }
+__device__ __forceinline__ float gelu_f(float z) { return z * gelu_eval(z).cdf; }
+__device__ __forceinline__ float gelu_d(float z) { GeluEval g = gelu_eval(z); return fmaf(z, g.pdf, g.cdf); }
 
 struct FusedParams {
     int N, L, T;
@@ -152,11 +175,7 @@ __device__ __forceinline__ void store8(uint8_t* a_hi, uint8_t* a_lo, int row, in
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        umma::split_bf16(v[2 * i], h0, l0);
-        umma::split_bf16(v[2 * i + 1], h1, l1);
-        h[i] = umma::pack2(h0, h1);
-        l[i] = umma::pack2(l0, l1);
+        umma::split2_bf16(v[2 * i], v[2 * i + 1], h[i], l[i]);
     }
     int off = (row >> 3) * kSBO_A + kcore * kLBO + (row & 7) * 16;
     *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(h[0], h[1], h[2], h[3]);

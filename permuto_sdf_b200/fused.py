@@ -115,3 +115,65 @@ class _FusedSDFTrainFn(torch.autograd.Function):
              zcat[3], acat[0], acat[1], acat[2], acat[3], gb[0], gb[1], gb[2], gb[3])
         gW = [(zcat[l].t() @ acat[l])[:dims_n[l], :dims_k[l]] for l in range(4)]     # plain library GEMMs [Np, 2N] x [2N, Kp]
         return (None, g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
+
+
+# ================================================================================================ NeuS compositing + losses
+class _NeusRenderLossFn(torch.autograd.Function):
+    """psdf_neus_render_loss_forward / _backward (csrc/neus_fused.cu): alpha, transmittance, weights, integration and the
+    rgb / mask / eikonal loss terms of one training iteration in a single launch each way
+    (volume_rendering_modules.py:129-176 + train_permuto_sdf.py:349-383)."""
+
+    @staticmethod
+    def forward(ctx, rsp, sdf, grad, rgb, inv_s, bg_rgb, cos_anneal, gt_rgb, gt_mask, hit, w_eik, w_mask):
+        R = rsp.ray_start_end_idx.shape[0]
+        N = sdf.shape[0]
+        dev = sdf.device
+        alpha = torch.empty(N, device=dev)
+        T = torch.empty(N, device=dev)
+        w = torch.empty(N, 1, device=dev)
+        pred = torch.empty(R, 3, device=dev)
+        wsum = torch.empty(R, 1, device=dev)
+        bgT = torch.empty(R, 1, device=dev)
+        ray_loss = torch.empty(R, 3, device=dev)
+        sdf_c, grad_c, rgb_c = sdf.detach().contiguous(), grad.detach().contiguous(), rgb.detach().contiguous()
+        inv_s_c = inv_s.detach().reshape(1).contiguous()
+        bg_c = None if bg_rgb is None else bg_rgb.detach().contiguous()
+        call("psdf_neus_render_loss_forward", *rsp._rsp(), sdf_c, grad_c, rgb_c, rsp.samples_dirs, rsp.samples_dt, inv_s_c, float(cos_anneal),
+             gt_rgb, gt_mask, hit, bg_c, alpha, T, w, pred, wsum, bgT, ray_loss)
+        scales = torch.tensor([1.0 / (3 * R), (w_mask / R) if gt_mask is not None else 0.0, w_eik / max(N, 1)], device=dev)
+        terms = ray_loss.sum(0)
+        loss = (terms * scales).sum()
+        ctx.rsp = rsp
+        ctx.cfg = (float(cos_anneal), gt_rgb, gt_mask, hit, 1.0 / (3 * R), (w_mask / R) if gt_mask is not None else 0.0, w_eik / max(N, 1))
+        ctx.has_bg = bg_rgb is not None
+        ctx.save_for_backward(sdf_c, grad_c, rgb_c, inv_s_c, bg_c, alpha, T, pred, wsum, bgT)
+        ctx.mark_non_differentiable(pred, wsum, w, terms)
+        return loss, pred, wsum, w, terms
+
+    @staticmethod
+    def backward(ctx, g_loss, *_):
+        sdf, grad, rgb, inv_s, bg, alpha, T, pred, wsum, bgT = ctx.saved_tensors
+        rsp = ctx.rsp
+        cos_anneal, gt_rgb, gt_mask, hit, s_rgb, s_mask, s_eik = ctx.cfg
+        g_sdf = torch.empty_like(sdf)
+        g_grad = torch.empty_like(grad)
+        g_rgb = torch.empty_like(rgb)
+        g_bg = torch.empty_like(bg) if ctx.has_bg and ctx.needs_input_grad[5] else None
+        g_inv = torch.zeros(1, device=sdf.device) if ctx.needs_input_grad[4] else None
+        call("psdf_neus_render_loss_backward", *rsp._rsp(), sdf, grad, rgb, rsp.samples_dirs, rsp.samples_dt, inv_s, cos_anneal, gt_rgb, gt_mask,
+             hit, bg, alpha, T, pred, wsum, bgT, g_loss.reshape(1).contiguous(), s_rgb, s_mask, s_eik, g_sdf, g_grad, g_rgb, g_bg, g_inv)
+        ctx.rsp = None
+        return (None, g_sdf, g_grad, g_rgb, None if g_inv is None else g_inv.reshape(()), g_bg, None, None, None, None, None, None)
+
+
+def neus_render_loss(rsp, sdf, sdf_gradients, rgb_samples, inv_s, cos_anneal_ratio, gt_rgb, gt_mask, hit, eikonal_weight, mask_weight,
+                     bg_rgb=None):
+    """-> (loss = rgb L1 + eikonal_weight * eikonal + mask_weight * BCE, pred_rgb [R,3], weights_sum [R,1], weights [N,1],
+    terms [3] = per-term sums). `inv_s` is the un-clipped 0-d tensor of SingleVarianceNetwork; `hit` bool/u8 [R] or None."""
+    load_library()
+    f = lambda t: None if t is None else t.detach().reshape(-1).contiguous().float()
+    hit_u8 = None if hit is None else hit.detach().reshape(-1).to(torch.uint8)
+    if sdf.shape[0] != rsp.samples_dirs.shape[0]:
+        raise ValueError("neus_render_loss: sdf must have one row per packed sample")
+    return _NeusRenderLossFn.apply(rsp, sdf.reshape(-1), sdf_gradients, rgb_samples, inv_s, bg_rgb, cos_anneal_ratio,
+                                   gt_rgb.detach().contiguous(), f(gt_mask), hit_u8, float(eikonal_weight), float(mask_weight))

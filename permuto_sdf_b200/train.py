@@ -92,7 +92,9 @@ def importance_sampling_sdf_model(model_sdf, rsp, ray_origins, ray_dirs, ray_t_e
 
 
 def run_net(with_mask, hyperparams, ray_origins, ray_dirs, img_indices, model_sdf, model_rgb, model_bg, model_colorcal, occupancy_grid,
-            iter_nr_for_anneal, cos_anneal_ratio, forced_variance):
+            iter_nr_for_anneal, cos_anneal_ratio, forced_variance, fused_loss=None):
+    """train_permuto_sdf.py:88-177. With `fused_loss` (dict: gt_rgb, gt_mask, hit, w_eik, w_mask) the NeuS compositing and the
+    rgb / mask / eikonal losses run in the fused kernel pair (csrc/neus_fused.cu); the result lands in fused_loss['loss']."""
     with torch.no_grad():
         _, _, _, ray_t_exit, _ = model_sdf.boundary_primitive.ray_intersection(ray_origins, ray_dirs)
         fg, bg = create_samples(with_mask, hyperparams, ray_origins, ray_dirs, model_sdf.training, occupancy_grid,
@@ -106,6 +108,25 @@ def run_net(with_mask, hyperparams, ray_origins, ray_dirs, img_indices, model_sd
         sdf_gradients = torch.zeros_like(ray_origins)
         weights_sum = torch.zeros_like(ray_origins)[:, 0:1]
         bg_transmittance = torch.ones_like(ray_origins)[:, 0:1]
+    elif fused_loss is not None:
+        sdf, sdf_gradients, geom_feat = model_sdf.get_sdf_and_gradient(fg.samples_pos, iter_nr_for_anneal)
+        rgb_samples = model_rgb(fg.samples_pos, fg.samples_dirs, sdf_gradients, geom_feat, iter_nr_for_anneal, model_colorcal, img_indices,
+                                fg.ray_start_end_idx)
+        vr = model_rgb.volume_renderer_neus
+        inv_s = vr.deviation_network(forced_variance)
+        vr.last_inv_s = inv_s.detach().clip(1e-6, 1e6)
+        bg_rgb = None
+        if not with_mask and bg is not None and bg.samples_pos_4d.shape[0] != 0:
+            rgb_bg, density_bg = model_bg(bg.samples_pos_4d, bg.samples_dirs, iter_nr_for_anneal, model_colorcal, img_indices,
+                                          ray_start_end_idx=bg.ray_start_end_idx)
+            weights_bg, _, _ = model_bg.volume_renderer_nerf.compute_weights(bg, density_bg.view(-1, 1))
+            bg_rgb = model_bg.volume_renderer_nerf.integrate(bg, rgb_bg, weights_bg)
+        from .fused import neus_render_loss
+        loss, pred_rgb, weights_sum, _, terms = neus_render_loss(fg, sdf, sdf_gradients, rgb_samples, inv_s, cos_anneal_ratio,
+                                                                 fused_loss["gt_rgb"], fused_loss["gt_mask"], fused_loss["hit"],
+                                                                 fused_loss["w_eik"], fused_loss["w_mask"], bg_rgb=bg_rgb)
+        fused_loss["loss"], fused_loss["terms"] = loss, terms
+        return pred_rgb, None, None, sdf_gradients, weights_sum, fg
     else:
         sdf, sdf_gradients, geom_feat = model_sdf.get_sdf_and_gradient(fg.samples_pos, iter_nr_for_anneal)
         rgb_samples = model_rgb(fg.samples_pos, fg.samples_dirs, sdf_gradients, geom_feat, iter_nr_for_anneal, model_colorcal, img_indices,
@@ -213,8 +234,9 @@ class Trainer:
     per-iteration step of train_permuto_sdf.py:311-422 (after sphere init), with `--with_mask` semantics."""
 
     def __init__(self, hyperparams=None, nr_levels=24, capacity=2 ** 18, sdf_hidden=32, nr_images=8, occupancy_resolution=256,
-                 seed=0, with_colorcal=True, optimizer="adamw", fused_inference=True, fused_training=True):
+                 seed=0, with_colorcal=True, optimizer="adamw", fused_inference=True, fused_training=True, fused_render=True):
         torch.manual_seed(seed)
+        self.fused_render = fused_render
         self._fused_inference = fused_inference
         self.hp = hyperparams or HyperParams()
         self.aabb = Sphere(0.5, [0, 0, 0])
@@ -259,13 +281,23 @@ class Trainer:
         forced_variance = map_range_val(iter_nr_for_anneal, 0.0, hp.forced_variance_finish_iter, 0.3, hp.forced_variance_finish)
         with torch.no_grad():
             _, _, _, _, does_hit = self.aabb.ray_intersection(ray_origins, ray_dirs)
+        fl = None
+        if self.fused_render:
+            fl = dict(gt_rgb=gt_rgb, gt_mask=gt_mask if hp.with_mask else None, hit=does_hit, w_eik=hp.eikonal_weight, w_mask=hp.mask_weight,
+                      loss=None)
         pred_rgb, _, _, sdf_gradients, weights_sum, fg = run_net(hp.with_mask, hp, ray_origins, ray_dirs, img_indices, self.model_sdf,
                                                                  self.model_rgb, self.model_bg, self.model_colorcal, self.occupancy_grid,
-                                                                 iter_nr_for_anneal, cos_anneal_ratio, forced_variance)
-        loss_rgb = rgb_loss(gt_rgb, pred_rgb, does_hit)
-        loss = loss_rgb
-        loss_eik = eikonal_loss(sdf_gradients)
-        loss = loss + loss_eik * hp.eikonal_weight
+                                                                 iter_nr_for_anneal, cos_anneal_ratio, forced_variance, fused_loss=fl)
+        fused_done = fl is not None and fl["loss"] is not None
+        if fused_done:
+            loss = fl["loss"]      # rgb L1 + eikonal + mask terms, already weighted
+            nr = max(fg.samples_pos.shape[0], 1)
+            loss_rgb, loss_eik = fl["terms"][0] / (3.0 * ray_origins.shape[0]), fl["terms"][2] / nr
+        else:
+            loss_rgb = rgb_loss(gt_rgb, pred_rgb, does_hit)
+            loss = loss_rgb
+            loss_eik = eikonal_loss(sdf_gradients)
+            loss = loss + loss_eik * hp.eikonal_weight
         gw_curv = map_range_val(iter_nr_for_anneal, hp.iter_start_reduce_curv, hp.iter_finish_reduce_curv, 1.0, 0.0)
         loss_curv = torch.zeros((), device=loss.device)
         if gw_curv > 0.0 and fg.samples_pos.shape[0] != 0:
@@ -280,7 +312,7 @@ class Trainer:
         loss_lip = self.model_rgb.mlp.lipshitz_bound_full()
         if iter_nr_for_anneal >= hp.iter_start_reduce_curv:
             loss = loss + loss_lip.mean() * hp.lipshitz_weight
-        if hp.with_mask:
+        if hp.with_mask and not fused_done:
             loss = loss + F.binary_cross_entropy(weights_sum.clip(1e-3, 1.0 - 1e-3), gt_mask) * hp.mask_weight
         self.last = dict(loss_rgb=loss_rgb.detach(), loss_eikonal=loss_eik.detach(), loss_curvature=loss_curv.detach(),
                          nr_samples=fg.samples_pos.shape[0], fg=fg)

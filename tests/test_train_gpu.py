@@ -142,3 +142,36 @@ def test_sphere_trace_analytic(cuda):
     # without a grid: one sample per ray
     pts2, _, _, _, rsp2 = sphere_trace(30, to, td, model, False, 0.9, 2e-4, None)
     assert pts2.shape[0] == 2000 and rsp2.rays_have_equal_nr_of_samples
+
+
+def test_fused_render_loss_equals_modular_iteration(trainer):
+    """one whole iteration (sampling -> models -> compositing -> losses -> backward) with the fused NeuS compositing + loss
+    kernels against the same iteration on the per-op kernels + torch losses; identical samples (RNG states restored)"""
+    from permuto_sdf import OccupancyGrid, PermutoSDF, RaySampler, VolumeRendering
+
+    class Reel:
+        pass
+    rgb, mask, K, tf = scenes.synthetic_reel(nimg=4, H=60, W=80)
+    reel = Reel()
+    reel.rgb_reel, reel.mask_reel, reel.K_reel, reel.tf_world_cam_reel = [torch.from_numpy(a).cuda() for a in (rgb, mask, K, tf)]
+    o, d, gt, gm, img = PermutoSDF.random_rays_from_reel(reel, 256)
+    rngs = [OccupancyGrid.m_rng, RaySampler.m_rng, VolumeRendering.m_rng]
+    states = [(r.state, r.inc) for r in rngs]
+    tstate, cstate = torch.get_rng_state(), torch.cuda.get_rng_state()
+    res = {}
+    for mode in (True, False):
+        for r, (s, i) in zip(rngs, states):
+            r.state, r.inc = s, i
+        torch.set_rng_state(tstate); torch.cuda.set_rng_state(cstate)
+        trainer.fused_render = mode
+        trainer.optimizer.zero_grad(set_to_none=False)
+        loss = trainer.losses(o, d, gt, gm, img, 3000)
+        loss.backward()
+        res[mode] = (float(loss), trainer.last["nr_samples"], trainer.model_sdf.encoding.lattice_values.grad.clone(),
+                     trainer.model_rgb.encoding.lattice_values.grad.clone(), trainer.model_rgb.mlp.layers[0].weight.grad.clone()
+                     if hasattr(trainer.model_rgb.mlp, "layers") else None)
+    trainer.fused_render = True
+    assert res[True][1] == res[False][1] and res[True][1] > 1000
+    assert abs(res[True][0] - res[False][0]) / abs(res[False][0]) < 1e-4
+    assert rel(res[True][2], res[False][2]) < 1e-3
+    assert rel(res[True][3], res[False][3]) < 1e-3
