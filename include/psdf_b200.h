@@ -13,7 +13,9 @@
  *     `[3]` (small host arrays passed by the caller); no allocation happens inside the library;
  *   - `stream` is a cudaStream_t; kernels are asynchronous on it; the library never synchronises;
  *   - return value: 0 = ok, <0 = error (PSDF_ERR_*); no global state: RNG state is passed explicitly
- *     as the (state, inc) pair of a pcg32 generator (kernels/permuto_sdf/pcg32.h:45-171);
+ *     as the (state, inc) pair of a pcg32 generator (kernels/permuto_sdf/pcg32.h:45-171). rng_inc == 0 (never a
+ *     valid pcg32 stream) marks rng_state as a DEVICE pointer to uint64_t[2] = {state, inc}: the generator then lives
+ *     in device memory, is advanced with psdf_rng_advance_dev, and the call can be replayed from a CUDA graph;
  *   - packed ray containers follow RaySamplesPacked (include/permuto_sdf/RaySamplesPacked.cuh:7-46):
  *     ray_start_end is int32 [R,2] = [start,end); `equal`/`fixed_n` is the rays_have_equal_nr_of_samples
  *     fast path; rays with end > max_nr_samples or zero samples are skipped
@@ -89,6 +91,10 @@ int psdf_sampler_bg(int nr_rays, int n_per_ray, const float* origins, const floa
                     int contract, float* s3, float* s4, float* s_dirs, float* s_z, float* s_dt, float* ray_fixed_dt,
                     int* ray_start_end, void* stream);
 
+/* device-resident generator: state <- state advanced by `delta` draws (the reference advances its static generators by 2^32
+ * after every jittered call, e.g. src/OccupancyGrid.cu:254) */
+int psdf_rng_advance_dev(uint64_t* rng_dev, long long delta, void* stream);
+
 /* ---------------------------------------------------------------- RaySamplesPacked (src/RaySamplesPacked.cu:44-146) */
 long long psdf_packed_compact_workspace_bytes(int nr_rays);
 /* compute_exact_nr_samples without the host sync: total_dev <- sum(end-start) */
@@ -142,16 +148,19 @@ int psdf_vr_volume_render_nerf_backward(PSDF_RSP, const float* grad_pred_rgb, co
  * gt_mask [R] or NULL, hit [R] u8 or NULL, bg_rgb [R,3] or NULL (pred += bg_T * bg_rgb).
  * ray_loss [R,3] = {sum_c |gt-pred| * hit, BCE(clip(w_sum,1e-3,1-1e-3), mask), sum_i (|grad_i|-1)^2}. */
 int psdf_neus_render_loss_forward(PSDF_RSP, const float* sdf, const float* grad, const float* rgb, const float* dirs, const float* dt,
-                                  const float* inv_s_dev, float cos_anneal_ratio, const float* gt_rgb, const float* gt_mask,
-                                  const uint8_t* hit, const float* bg_rgb, float* alpha, float* transmittance, float* weights,
+                                  const float* inv_s_dev, float cos_anneal_ratio, const float* cos_anneal_dev, const float* gt_rgb,
+                                  const float* gt_mask, const uint8_t* hit, const float* bg_rgb, float* alpha, float* transmittance, float* weights,
                                   float* pred_rgb, float* weights_sum, float* bg_transmittance, float* ray_loss, void* stream);
 /* d loss / d {sdf, grad, rgb, bg_rgb, inv_s} for loss = g_total * (scale_rgb * sum rgb-term + scale_mask * sum bce + scale_eik * sum eik);
- * g_total_dev [1] device scalar or NULL (=1); g_bg_rgb / g_inv_s may be NULL; g_inv_s is accumulated (+=). */
+ * g_total_dev [1] device scalar or NULL (=1); g_bg_rgb / g_inv_s may be NULL; g_inv_s is accumulated (+=).
+ * cos_anneal_dev [1] (both calls) overrides cos_anneal_ratio when not NULL; nr_samples_dev [1] int, when not NULL, divides
+ * scale_eik on the device (static-capacity containers under CUDA-graph replay, where the sample count is not known on the host). */
 int psdf_neus_render_loss_backward(PSDF_RSP, const float* sdf, const float* grad, const float* rgb, const float* dirs, const float* dt,
-                                   const float* inv_s_dev, float cos_anneal_ratio, const float* gt_rgb, const float* gt_mask,
-                                   const uint8_t* hit, const float* bg_rgb, const float* alpha, const float* transmittance,
+                                   const float* inv_s_dev, float cos_anneal_ratio, const float* cos_anneal_dev, const float* gt_rgb,
+                                   const float* gt_mask, const uint8_t* hit, const float* bg_rgb, const float* alpha, const float* transmittance,
                                    const float* pred_rgb, const float* weights_sum, const float* bg_transmittance,
-                                   const float* g_total_dev, float scale_rgb, float scale_mask, float scale_eik, float* g_sdf,
+                                   const float* g_total_dev, float scale_rgb, float scale_mask, float scale_eik,
+                                   const int* nr_samples_dev, float* g_sdf,
                                    float* g_grad, float* g_rgb, float* g_bg_rgb, float* g_inv_s, void* stream);
 
 /* ---------------------------------------------------------------- PermutoSDF statics (include/permuto_sdf/PermutoSDF.cuh:46-55) */
@@ -201,12 +210,16 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
                             float* gb3, void* stream);
 /* ---------------------------------------------------------------- dense fused AdamW (torch.optim.AdamW / apex FusedAdam math,
  * train_permuto_sdf.py:293-304); step >= 1 is the incremented step count; grad is multiplied by grad_scale and, when
- * zero_grad != 0, reset to zero in the same pass. Pointers 16-byte aligned. */
+ * zero_grad != 0, reset to zero in the same pass. Pointers 16-byte aligned. step_dev [1] (device int32), when not NULL,
+ * replaces `step` so that the call can be replayed from a CUDA graph. */
 int psdf_adamw_step(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, int step, float grad_scale, int zero_grad, void* stream);
+                    float eps, float weight_decay, int step, const int* step_dev, float grad_scale, int zero_grad, void* stream);
 
 /* self-test of the tensor-core path: D[128,N] = A[128,K] * B[N,K]^T (N,K <= 64) */
 int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream);
+/* self-test of the weight-gradient product: D[M,N] = A[128,M]^T * B[128,N] (M,N <= 64) with the sample axis as the MMA K
+ * dimension and MN-major operands; dump [128,64] = every TMEM lane x column of the accumulator region */
+int psdf_debug_umma_gemm_tn(int M, int N, const float* A, const float* B, float* dump, void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,6 +40,11 @@ struct Pcg32 {
     __host__ __device__ Pcg32() : state(0x853c49e6748fea9bULL), inc(0xda3e39cb94b95bdbULL) {}
     __host__ __device__ Pcg32(uint64_t s, uint64_t i) : state(s), inc(i) {}
 
+    // device-resident generator (CUDA-graph replay): inc == 0 is not a valid pcg32 stream, it marks `state` as a device
+    // pointer to {state, inc}; kernels call resolve() once before drawing
+    __device__ __forceinline__ void resolve() {
+        if (inc == 0) { const uint64_t* p = reinterpret_cast<const uint64_t*>(state); state = p[0]; inc = p[1]; }
+    }
     __host__ __device__ __forceinline__ uint32_t next_uint() {
         uint64_t old = state;
         state = old * kMult + inc;

@@ -101,29 +101,24 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
                     for (int r = 0; r < 4; r++) { float wr = s.bary[r] * w; a0 = fmaf(v[r].x, wr, a0); a1 = fmaf(v[r].y, wr, a1); }
                     fv[2 * q] = a0; fv[2 * q + 1] = a1;
                     if (TAN) {
+                        // d feat / d x_j = w scale_j / 4 * sum_i E[i][j] G_i, with G_i = u_{rank_i}, u_k = d feat / d D_k
+                        // (fused_common.cuh by_rank) and E the elevation matrix rows {1,1,1},{-1,1,1},{0,-2,1},{0,0,-3}
+                        float2 u[4], G[4];
+                        u[0] = make_float2(v[3].x - v[0].x, v[3].y - v[0].y);
+                        u[1] = make_float2(v[2].x - v[3].x, v[2].y - v[3].y);
+                        u[2] = make_float2(v[1].x - v[2].x, v[1].y - v[2].y);
+                        u[3] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
 #pragma unroll
-                        for (int j = 0; j < 3; j++) {
-                            // tangent of the weights along e_j: same rank scatter applied to the elevated direction
-                            float de[4], sm = 0.f;
-#pragma unroll
-                            for (int i = 3; i > 0; i--) {
-                                float dc = (i - 1 == j) ? lc->scale[l * 4 + j] : 0.f;
-                                de[i] = sm - (float)i * dc; sm += dc;
-                            }
-                            de[0] = sm;
-                            float db[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                            for (int i = 0; i < 4; i++) {
-                                float dl = de[i] * 0.25f;
-#pragma unroll
-                                for (int r = 0; r < 5; r++) { if (r == 3 - s.rank[i]) db[r] += dl; if (r == 4 - s.rank[i]) db[r] -= dl; }
-                            }
-                            db[0] += db[4];
-                            float t0 = 0.f, t1 = 0.f;
-#pragma unroll
-                            for (int r = 0; r < 4; r++) { float c = db[r] * w; t0 = fmaf(v[r].x, c, t0); t1 = fmaf(v[r].y, c, t1); }
-                            ft[j][2 * q] = t0; ft[j][2 * q + 1] = t1;
+                        for (int i = 0; i < 4; i++) {
+                            const int rk = s.rank[i];
+                            G[i].x = rk == 0 ? u[0].x : (rk == 1 ? u[1].x : (rk == 2 ? u[2].x : u[3].x));
+                            G[i].y = rk == 0 ? u[0].y : (rk == 1 ? u[1].y : (rk == 2 ? u[2].y : u[3].y));
                         }
+                        const float c0 = 0.25f * w * lc->scale[l * 4], c1 = 0.25f * w * lc->scale[l * 4 + 1], c2 = 0.25f * w * lc->scale[l * 4 + 2];
+                        const float s01x = G[0].x + G[1].x, s01y = G[0].y + G[1].y;
+                        ft[0][2 * q] = c0 * (G[0].x - G[1].x); ft[0][2 * q + 1] = c0 * (G[0].y - G[1].y);
+                        ft[1][2 * q] = c1 * fmaf(-2.0f, G[2].x, s01x); ft[1][2 * q + 1] = c1 * fmaf(-2.0f, G[2].y, s01y);
+                        ft[2][2 * q] = c2 * fmaf(-3.0f, G[3].x, s01x + G[2].x); ft[2][2 * q + 1] = c2 * fmaf(-3.0f, G[3].y, s01y + G[2].y);
                     }
                 }
             } else {
@@ -182,12 +177,13 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
                 if (!last) {
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
+                        const GeluEval ge = gelu_eval(z[i]);
                         if (TAN) {
-                            float g1 = gelu_d(z[i]);
+                            const float g1 = fmaf(z[i], ge.pdf, ge.cdf);
 #pragma unroll
                             for (int j = 0; j < 3; j++) tz[j][i] *= g1;
                         }
-                        z[i] = gelu_f(z[i]);
+                        z[i] *= ge.cdf;
                     }
                     store8(s_a, s_a + kATileBytes, row, 2 * c, z);
                     store8(s_a, s_a + kATileBytes, row, 2 * c + 1, z + 8);
@@ -277,10 +273,92 @@ __global__ void __launch_bounds__(kTile) k_debug_gemm(int N, int K, const float*
     if (warp == 0) umma::tmem_dealloc(tmem_base, 64);
 }
 
+// D[M x N] = A^T B over the 128 rows of two operand tiles (A [128 x M], B [128 x N], both stored like every activation tile:
+// row = sample, 16-byte core rows along the columns), i.e. the weight-gradient product dW = zbar^T a with the sample axis as the
+// MMA K dimension and both operands MN-major. `dump` receives all 128 TMEM lanes x N columns so that the accumulator layout of
+// an M = 64 instruction can be read off on the host.
+__global__ void __launch_bounds__(kTile) k_debug_gemm_tn(int M, int N, const float* __restrict__ A, const float* __restrict__ B,
+                                                         float* __restrict__ dump) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* a_hi = smem;
+    uint8_t* a_lo = a_hi + kATileBytes;
+    uint8_t* b_hi = a_lo + kATileBytes;
+    uint8_t* b_lo = b_hi + kATileBytes;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(b_lo + kATileBytes);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bar + 1);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) { umma::mbar_init(bar, 1); umma::mbar_fence_init(); }
+    for (int kc = 0; kc < 8; kc++) {
+        float va[8], vb[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            int c = kc * 8 + i;
+            va[i] = c < M ? A[tid * M + c] : 0.f;
+            vb[i] = c < N ? B[tid * N + c] : 0.f;
+        }
+        store8(a_hi, a_lo, tid, kc, va);
+        store8(b_hi, b_lo, tid, kc, vb);
+    }
+    __syncthreads();
+    if (warp == 0) umma::tmem_alloc(slot, 64);
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *slot;
+    // clear the accumulator columns first so that lanes the MMA does not write read back as zero
+    {
+        float z[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) z[i] = 0.f;
+        for (int c = 0; c < 4; c++) umma::tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 16, z);
+        umma::tmem_st_wait();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+        umma::fence_after_sync();
+        const int Mp = pad16(M), Np = pad16(N);
+        const uint32_t idesc = umma::make_idesc_mn(Mp, Np, umma::kFmtBF16);
+        const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo), bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
+        for (int kk = 0; kk < kTile / 16; kk++) {
+            const uint32_t ko = kk * 2 * kSBO_A;          // 16 samples = 2 eight-row groups
+            // MN-major, no swizzle: LBO = stride between 8-sample groups (K), SBO = stride between 8-column cores (MN)
+            uint64_t dah = umma::make_desc(ah + ko, kSBO_A, kLBO), dal = umma::make_desc(al + ko, kSBO_A, kLBO);
+            uint64_t dbh = umma::make_desc(bh + ko, kSBO_A, kLBO), dbl = umma::make_desc(bl + ko, kSBO_A, kLBO);
+            umma::mma_bf16(tmem_base, dah, dbh, idesc, kk > 0 ? 1u : 0u);
+            umma::mma_bf16(tmem_base, dah, dbl, idesc, 1u);
+            umma::mma_bf16(tmem_base, dal, dbh, idesc, 1u);
+        }
+        umma::commit(bar);
+    }
+    umma::mbar_wait(bar, 0);
+    umma::fence_after_sync();
+    for (int c = 0; c < 4; c++) {
+        float z[16];
+        umma::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c * 16, z);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i++) dump[tid * 64 + c * 16 + i] = z[i];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_base, 64);
+}
+
 #define ST ((cudaStream_t)stream)
 }  // namespace
 
 extern "C" {
+
+int psdf_debug_umma_gemm_tn(int M, int N, const float* A, const float* B, float* dump, void* stream) {
+    if (M < 1 || M > 64 || N < 1 || N > 64) return PSDF_ERR_ARG;
+    int smem = 4 * kATileBytes + 64;
+    cudaFuncSetAttribute(k_debug_gemm_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_debug_gemm_tn<<<1, kTile, smem, ST>>>(M, N, A, B, dump);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
 
 long long psdf_sdf_mlp_blob_bytes(int in_dim, int hidden, int out_dim) {
     MlpGeom g = make_geom(in_dim, hidden, out_dim);

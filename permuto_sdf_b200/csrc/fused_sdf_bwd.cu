@@ -61,21 +61,24 @@ __device__ __forceinline__ float2 add_peers2(unsigned peers, float2 x, int lane)
 __device__ __forceinline__ void red_v2(float* addr, float2 v) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y) : "memory");
 }
-// tangent of the barycentric weights along the (scaled) direction dcf
-__device__ __forceinline__ void bary_tangent3(const float* dcf, const Simplex3& s, float* db) {
-    float de[4], sm = 0.f;
+// column sums of 16 per-lane values over the 32 lanes of a warp with 16 shuffles (halving butterfly): afterwards both
+// lanes of the pair {2p, 2p+1} hold the sum of column `col` = bit-reversal-free index built from lane bits 4..1.
+__device__ __forceinline__ float colsum16(const float* v, int lane, int& col) {
+    float a[8], b[4], c[2], d;
+    bool up = lane & 16;
 #pragma unroll
-    for (int i = 3; i > 0; i--) { de[i] = sm - (float)i * dcf[i - 1]; sm += dcf[i - 1]; }
-    de[0] = sm;
+    for (int i = 0; i < 8; i++) { float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i]; a[i] = keep + __shfl_xor_sync(kFull, send, 16); }
+    up = lane & 8;
 #pragma unroll
-    for (int r = 0; r < 5; r++) db[r] = 0.f;
+    for (int i = 0; i < 4; i++) { float send = up ? a[i] : a[i + 4], keep = up ? a[i + 4] : a[i]; b[i] = keep + __shfl_xor_sync(kFull, send, 8); }
+    up = lane & 4;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float dl = de[i] * 0.25f;
-#pragma unroll
-        for (int r = 0; r < 5; r++) { if (r == 3 - s.rank[i]) db[r] += dl; if (r == 4 - s.rank[i]) db[r] -= dl; }
-    }
-    db[0] += db[4];
+    for (int i = 0; i < 2; i++) { float send = up ? b[i] : b[i + 2], keep = up ? b[i + 2] : b[i]; c[i] = keep + __shfl_xor_sync(kFull, send, 4); }
+    up = lane & 2;
+    { float send = up ? c[0] : c[1], keep = up ? c[1] : c[0]; d = keep + __shfl_xor_sync(kFull, send, 2); }
+    d += __shfl_xor_sync(kFull, d, 1);
+    col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    return d;
 }
 // 8 consecutive fp32 of a row to global (two float4 stores)
 __device__ __forceinline__ void st8(float* dst, const float* v) {
@@ -220,9 +223,10 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                     umma::tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; i++) {
-                        float zz = z[i] + s_bias[l * 64 + c * 16 + i];
-                        z[i] = gelu_f(zz);
-                        tz[i] *= gelu_d(zz);
+                        const float zz = z[i] + s_bias[l * 64 + c * 16 + i];
+                        const GeluEval ge = gelu_eval(zz);
+                        z[i] = zz * ge.cdf;
+                        tz[i] *= fmaf(zz, ge.pdf, ge.cdf);
                     }
                     store8(s_t, s_t + kATileBytes, row, 2 * c, z);
                     store8(s_t, s_t + kATileBytes, row, 2 * c + 1, z + 8);
@@ -265,12 +269,13 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                 store8(s_t, s_t + kATileBytes, row, c, zb);
                 store8(s_t + 2 * kATileBytes, s_t + 3 * kATileBytes, row, c, tb);
                 if (valid) { st8(sp.zcat[3] + (size_t)n * Np + c * 8, zb); st8(sp.zcat[3] + (Nn + n) * Np + c * 8, tb); }
+                {                                                  // bias gradient: column sums over the warp's 32 rows
+                    float z16[16];
 #pragma unroll
-                for (int i = 0; i < 8; i++) {                      // bias gradient: column sums over the warp's 32 rows
-                    float sacc = zb[i];
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(kFull, sacc, o);
-                    if (lane == 0) atomicAdd(&s_gb[3 * 64 + c * 8 + i], sacc);
+                    for (int i = 0; i < 8; i++) { z16[i] = zb[i]; z16[i + 8] = 0.f; }
+                    int col;
+                    const float cs = colsum16(z16, lane, col);
+                    if (!(lane & 1) && col < 8) atomicAdd(&s_gb[3 * 64 + c * 8 + col], cs);
                 }
             }
         }
@@ -308,7 +313,8 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
                             float zz = z[i] + s_bias[(l - 1) * 64 + c * 16 + i];
-                            float g1 = gelu_d(zz), g2 = gelu_d2(zz);
+                            const GeluEval ge = gelu_eval(zz);
+                            const float g1 = fmaf(zz, ge.pdf, ge.cdf), g2 = ge.pdf * (2.0f - zz * zz);
                             float zb = g1 * ab[i] + g2 * tz[i] * tab_[i];
                             tab_[i] = g1 * tab_[i];
                             ab[i] = zb;
@@ -322,12 +328,14 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                             st8(sp.zcat[l - 1] + (size_t)n * Kp + c * 16, ab); st8(sp.zcat[l - 1] + (size_t)n * Kp + c * 16 + 8, ab + 8);
                             st8(sp.zcat[l - 1] + (Nn + n) * Kp + c * 16, tab_); st8(sp.zcat[l - 1] + (Nn + n) * Kp + c * 16 + 8, tab_ + 8);
                         }
+                        {                                              // bias gradient: column sums over the warp's 32 rows
+                            if (!valid) {
 #pragma unroll
-                        for (int i = 0; i < 16; i++) {
-                            float sacc = valid ? ab[i] : 0.f;
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(kFull, sacc, o);
-                            if (lane == 0) atomicAdd(&s_gb[(l - 1) * 64 + c * 16 + i], sacc);
+                                for (int i = 0; i < 16; i++) ab[i] = 0.f;
+                            }
+                            int col;
+                            const float cs = colsum16(ab, lane, col);
+                            if (!(lane & 1)) atomicAdd(&s_gb[(l - 1) * 64 + c * 16 + col], cs);
                         }
                     } else {
                         umma::tmem_ld_wait();

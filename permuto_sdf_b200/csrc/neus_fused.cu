@@ -44,7 +44,7 @@ __device__ __forceinline__ NeusSample neus_alpha(float sdf, float gx, float gy, 
 __global__ void __launch_bounds__(kThreads)
 k_neus_forward(int nr_rays, int max_nr_samples, const int* __restrict__ start_end, bool equal, int fixed_n, const float* __restrict__ sdf,
                const float* __restrict__ grad, const float* __restrict__ rgb, const float* __restrict__ dirs, const float* __restrict__ dt_,
-               const float* __restrict__ inv_s_dev, float cos_anneal, const float* __restrict__ gt_rgb, const float* __restrict__ gt_mask,
+               const float* __restrict__ inv_s_dev, float cos_anneal, const float* __restrict__ cos_anneal_dev, const float* __restrict__ gt_rgb, const float* __restrict__ gt_mask,
                const uint8_t* __restrict__ hit, const float* __restrict__ bg_rgb, float* __restrict__ alpha_out, float* __restrict__ T_out, float* __restrict__ w_out,
                float* __restrict__ pred_rgb, float* __restrict__ w_sum, float* __restrict__ bg_T, float* __restrict__ ray_loss /* [R,3] */) {
     int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -53,6 +53,7 @@ k_neus_forward(int nr_rays, int max_nr_samples, const int* __restrict__ start_en
     RayRange rr = ray_range(ray, start_end, equal, fixed_n);
     bool skip = (rr.end > max_nr_samples) || (rr.n == 0);
     const float s = fminf(fmaxf(inv_s_dev[0], 1e-6f), 1e6f);
+    if (cos_anneal_dev) cos_anneal = cos_anneal_dev[0];
     float T = 1.0f, ax = 0.f, ay = 0.f, az = 0.f, ws = 0.f, eik = 0.f;
     if (!skip) {
         for (int base = 0; base < rr.n; base += 32) {
@@ -105,11 +106,11 @@ k_neus_forward(int nr_rays, int max_nr_samples, const int* __restrict__ start_en
 __global__ void __launch_bounds__(kThreads)
 k_neus_backward(int nr_rays, int max_nr_samples, const int* __restrict__ start_end, bool equal, int fixed_n, const float* __restrict__ sdf,
                 const float* __restrict__ grad, const float* __restrict__ rgb, const float* __restrict__ dirs, const float* __restrict__ dt_,
-                const float* __restrict__ inv_s_dev, float cos_anneal, const float* __restrict__ gt_rgb, const float* __restrict__ gt_mask,
+                const float* __restrict__ inv_s_dev, float cos_anneal, const float* __restrict__ cos_anneal_dev, const float* __restrict__ gt_rgb, const float* __restrict__ gt_mask,
                 const uint8_t* __restrict__ hit, const float* __restrict__ bg_rgb, const float* __restrict__ alpha_in,
                 const float* __restrict__ T_in, const float* __restrict__ pred_rgb, const float* __restrict__ w_sum,
                 const float* __restrict__ bg_T, const float* __restrict__ g_total_dev, float scale_rgb,
-                float scale_mask, float scale_eik, float* __restrict__ g_sdf, float* __restrict__ g_grad, float* __restrict__ g_rgb,
+                float scale_mask, float scale_eik, const int* __restrict__ nr_samples_dev, float* __restrict__ g_sdf, float* __restrict__ g_grad, float* __restrict__ g_rgb,
                 float* __restrict__ g_bg_rgb, float* __restrict__ g_inv_s) {
     int ray = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
@@ -121,6 +122,8 @@ k_neus_backward(int nr_rays, int max_nr_samples, const int* __restrict__ start_e
     const float s_raw = inv_s_dev[0];
     const float s = fminf(fmaxf(s_raw, 1e-6f), 1e6f);
     const bool s_active = (s_raw >= 1e-6f && s_raw <= 1e6f);
+    if (cos_anneal_dev) cos_anneal = cos_anneal_dev[0];
+    if (nr_samples_dev) scale_eik = scale_eik / (float)max(nr_samples_dev[0], 1);
     // upstream of the per-ray outputs
     float h = hit ? (hit[ray] ? 1.0f : 0.0f) : 1.0f;
     float gp[3];
@@ -203,28 +206,28 @@ inline int ray_blocks(int nr_rays) { return div_up((long long)nr_rays * 32, kThr
 extern "C" {
 int psdf_neus_render_loss_forward(int nr_rays, int max_nr_samples, const int* ray_start_end, int equal, int fixed_n, const float* sdf,
                                   const float* grad, const float* rgb, const float* dirs, const float* dt, const float* inv_s_dev,
-                                  float cos_anneal_ratio, const float* gt_rgb, const float* gt_mask, const uint8_t* hit, const float* bg_rgb,
+                                  float cos_anneal_ratio, const float* cos_anneal_dev, const float* gt_rgb, const float* gt_mask, const uint8_t* hit, const float* bg_rgb,
                                   float* alpha, float* transmittance, float* weights, float* pred_rgb, float* weights_sum, float* bg_transmittance,
                                   float* ray_loss, void* stream) {
     if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
     k_neus_forward<<<ray_blocks(nr_rays), kThreads, 0, ST>>>(nr_rays, max_nr_samples, ray_start_end, equal != 0, fixed_n, sdf, grad, rgb, dirs, dt,
-                                                            inv_s_dev, cos_anneal_ratio, gt_rgb, gt_mask, hit, bg_rgb, alpha, transmittance, weights,
+                                                            inv_s_dev, cos_anneal_ratio, cos_anneal_dev, gt_rgb, gt_mask, hit, bg_rgb, alpha, transmittance, weights,
                                                             pred_rgb, weights_sum, bg_transmittance, ray_loss);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }
 int psdf_neus_render_loss_backward(int nr_rays, int max_nr_samples, const int* ray_start_end, int equal, int fixed_n, const float* sdf,
                                    const float* grad, const float* rgb, const float* dirs, const float* dt, const float* inv_s_dev,
-                                   float cos_anneal_ratio, const float* gt_rgb, const float* gt_mask, const uint8_t* hit, const float* bg_rgb,
+                                   float cos_anneal_ratio, const float* cos_anneal_dev, const float* gt_rgb, const float* gt_mask, const uint8_t* hit, const float* bg_rgb,
                                    const float* alpha, const float* transmittance, const float* pred_rgb, const float* weights_sum,
                                    const float* bg_transmittance, const float* g_total_dev,
-                                   float scale_rgb, float scale_mask, float scale_eik, float* g_sdf, float* g_grad, float* g_rgb,
+                                   float scale_rgb, float scale_mask, float scale_eik, const int* nr_samples_dev, float* g_sdf, float* g_grad, float* g_rgb,
                                    float* g_bg_rgb, float* g_inv_s, void* stream) {
     if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
     k_neus_backward<<<ray_blocks(nr_rays), kThreads, 0, ST>>>(nr_rays, max_nr_samples, ray_start_end, equal != 0, fixed_n, sdf, grad, rgb, dirs, dt,
-                                                             inv_s_dev, cos_anneal_ratio, gt_rgb, gt_mask, hit, bg_rgb, alpha, transmittance,
-                                                             pred_rgb, weights_sum, bg_transmittance, g_total_dev, scale_rgb, scale_mask,
-                                                             scale_eik, g_sdf, g_grad, g_rgb, g_bg_rgb, g_inv_s);
+                                                             inv_s_dev, cos_anneal_ratio, cos_anneal_dev, gt_rgb, gt_mask, hit, bg_rgb, alpha,
+                                                             transmittance, pred_rgb, weights_sum, bg_transmittance, g_total_dev, scale_rgb,
+                                                             scale_mask, scale_eik, nr_samples_dev, g_sdf, g_grad, g_rgb, g_bg_rgb, g_inv_s);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }

@@ -14,8 +14,13 @@ using namespace psdf;
 namespace {
 __global__ void __launch_bounds__(256)
 k_adamw(long long n, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float lr,
-        float beta1, float beta2, float eps, float weight_decay, float bias_c1, float bias_c2_sqrt, float grad_scale, int zero_grad) {
+        float beta1, float beta2, float eps, float weight_decay, float bias_c1, float bias_c2_sqrt, const int* __restrict__ step_dev, float grad_scale, int zero_grad) {
     const long long n4 = n >> 2;
+    if (step_dev) {   // step count kept in device memory (CUDA-graph replay): bias corrections computed here
+        const float t = (float)step_dev[0];
+        bias_c1 = 1.0f - powf(beta1, t);
+        bias_c2_sqrt = sqrtf(1.0f - powf(beta2, t));
+    }
     const float decay = 1.0f - lr * weight_decay;
     const float step_size = lr / bias_c1;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -52,11 +57,12 @@ k_adamw(long long n, float* __restrict__ p, float* __restrict__ g, float* __rest
 }  // namespace
 
 extern "C" {
-// step >= 1 is the (already incremented) step count; pointers must be 16-byte aligned
+// step >= 1 is the (already incremented) step count, read from step_dev[0] instead when that is not NULL; pointers 16-byte aligned
 int psdf_adamw_step(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, int step, float grad_scale, int zero_grad, void* stream) {
+                    float eps, float weight_decay, int step, const int* step_dev, float grad_scale, int zero_grad, void* stream) {
     if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
-    if (step < 1) return PSDF_ERR_ARG;
+    if (step < 1 && !step_dev) return PSDF_ERR_ARG;
+    if (step < 1) step = 1;
     if ((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) != 0) return PSDF_ERR_ARG;
     double c1 = 1.0 - pow((double)beta1, (double)step);
     double c2 = 1.0 - pow((double)beta2, (double)step);
@@ -68,7 +74,7 @@ int psdf_adamw_step(long long n, float* param, float* grad, float* exp_avg, floa
     if (blocks < 1) blocks = 1;
     if (blocks > sms * 8) blocks = sms * 8;
     k_adamw<<<blocks, 256, 0, ST>>>(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, (float)c1, (float)sqrt(c2),
-                                   grad_scale, zero_grad);
+                                   step_dev, grad_scale, zero_grad);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }

@@ -72,10 +72,17 @@ __global__ void __launch_bounds__(kThreads) k_sphere_inside(int n, float radius,
     out[i] = sqrtf(x * x + y * y + z * z) < radius;
 }
 
+// advance a device-resident pcg32 {state, inc} (the host-side `rng.advance(2^32)` after every jittered call)
+__global__ void k_rng_advance(uint64_t* rng_dev, long long delta) {
+    Pcg32 r(rng_dev[0], rng_dev[1]);
+    r.advance(delta);
+    rng_dev[0] = r.state;
+}
 // ------------------------------------------------------------------------------------------------ Occupancy
 // OccupancyGridGPU.cuh:196-301
 __global__ void __launch_bounds__(kThreads) k_occ_grid_points(int n, GridGeom g, const int* __restrict__ idx, Pcg32 rng,
                                                               bool randomize, float* __restrict__ out) {
+    rng.resolve();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t v = idx ? (uint32_t)idx[i] : (uint32_t)i;
@@ -148,6 +155,7 @@ k_occ_samples_in_occupied(int nr_rays, GridGeom g, const float* __restrict__ ori
                           bool jitter, int slot_mode, float* __restrict__ s_pos, float* __restrict__ s_dirs,
                           float* __restrict__ s_z, float* __restrict__ s_dt, float* __restrict__ ray_fixed_dt,
                           int* __restrict__ start_end, int* __restrict__ cur_nr_samples) {
+    rng.resolve();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nr_rays) return;
     const int nv = g.V * g.V * g.V;
@@ -338,6 +346,7 @@ k_sampler_fg(int nr_rays, const float* __restrict__ origins, const float* __rest
              int slot_mode, float* __restrict__ s_pos, float* __restrict__ s_dirs, float* __restrict__ s_z,
              float* __restrict__ s_dt, float* __restrict__ ray_fixed_dt, int* __restrict__ start_end,
              int* __restrict__ cur_nr_samples) {
+    rng.resolve();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nr_rays) return;
     const float eps = 1e-6f;
@@ -407,6 +416,7 @@ k_sampler_bg(int nr_rays, int n_per_ray, const float* __restrict__ origins, cons
              bool contract, float* __restrict__ s3, float* __restrict__ s4, float* __restrict__ s_dirs,
              float* __restrict__ s_z, float* __restrict__ s_dt, float* __restrict__ ray_fixed_dt,
              int* __restrict__ start_end) {
+    rng.resolve();
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nr_rays) return;
     float ox = origins[3 * idx], oy = origins[3 * idx + 1], oz = origins[3 * idx + 2];
@@ -781,6 +791,13 @@ int psdf_sampler_bg(int nr_rays, int n_per_ray, const float* origins, const floa
                                                     sphere_center[1], sphere_center[2], Pcg32(rng_state, rng_inc),
                                                     randomize != 0, contract != 0, s3, s4, s_dirs, s_z, s_dt, ray_fixed_dt,
                                                     ray_start_end);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+
+int psdf_rng_advance_dev(uint64_t* rng_dev, long long delta, void* stream) {
+    if (!rng_dev || delta < 0) return PSDF_ERR_ARG;
+    k_rng_advance<<<1, 1, 0, ST>>>(rng_dev, delta);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }

@@ -180,6 +180,7 @@ k_importance_sample(int nr_rays, const float* __restrict__ origins, const float*
                     const int* __restrict__ start_end, const float* __restrict__ ray_fixed_dt, bool equal, int fixed_n,
                     const float* __restrict__ z, const float* __restrict__ cdf, int nr_imp, Pcg32 rng0, bool jitter,
                     float* __restrict__ o_pos, float* __restrict__ o_dirs, float* __restrict__ o_z) {
+    rng0.resolve();
     RAY_PROLOGUE();
     int ist = ray * nr_imp;
     float ox = origins[3 * ray], oy = origins[3 * ray + 1], oz = origins[3 * ray + 2];

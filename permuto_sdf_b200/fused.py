@@ -8,6 +8,7 @@ evaluations that need parameter gradients go through the differentiable modules 
 import torch
 
 from ._lib import call, load_library
+from .permuto_sdf import RaySamplesPacked
 
 
 class FusedSDF:
@@ -113,7 +114,13 @@ class _FusedSDFTrainFn(torch.autograd.Function):
         call("psdf_sdf_fused_backward", N, enc.nr_levels, enc.capacity, points, lattice.detach(), enc.scale_factor, enc.shift_tensor(), window,
              enc.concat_points_scaling, fused.hidden, fused.out_dim, fused.blob, c(g_sdf), c(g_grad), c(g_geom), g_lat, zcat[0], zcat[1], zcat[2],
              zcat[3], acat[0], acat[1], acat[2], acat[3], gb[0], gb[1], gb[2], gb[3])
-        gW = [(zcat[l].t() @ acat[l])[:dims_n[l], :dims_k[l]] for l in range(4)]     # plain library GEMMs [Np, 2N] x [2N, Kp]
+        # dW_l = zcat_l^T acat_l: a [Np, 2N] x [2N, Kp] library GEMM whose reduction dimension is the sample axis; split-K as a
+        # batched GEMM (one slab of samples per batch entry) so that it fills the GPU instead of 1-2 CTAs looping over 2N rows
+        S = 64 if (2 * N) % 64 == 0 and N >= 2048 else 1
+        gW = []
+        for l in range(4):
+            z3, a3 = zcat[l].view(S, -1, zcat[l].shape[1]), acat[l].view(S, -1, acat[l].shape[1])
+            gW.append(torch.bmm(z3.transpose(1, 2), a3).sum(0)[:dims_n[l], :dims_k[l]])
         return (None, g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
 
 
@@ -130,7 +137,7 @@ class _NeusRenderLossFn(torch.autograd.Function):
         dev = sdf.device
         alpha = torch.empty(N, device=dev)
         T = torch.empty(N, device=dev)
-        w = torch.empty(N, 1, device=dev)
+        w = torch.zeros(N, 1, device=dev)
         pred = torch.empty(R, 3, device=dev)
         wsum = torch.empty(R, 1, device=dev)
         bgT = torch.empty(R, 1, device=dev)
@@ -138,13 +145,22 @@ class _NeusRenderLossFn(torch.autograd.Function):
         sdf_c, grad_c, rgb_c = sdf.detach().contiguous(), grad.detach().contiguous(), rgb.detach().contiguous()
         inv_s_c = inv_s.detach().reshape(1).contiguous()
         bg_c = None if bg_rgb is None else bg_rgb.detach().contiguous()
-        call("psdf_neus_render_loss_forward", *rsp._rsp(), sdf_c, grad_c, rgb_c, rsp.samples_dirs, rsp.samples_dt, inv_s_c, float(cos_anneal),
+        # schedule values / sample count that live on the device (static-capacity containers under CUDA-graph replay)
+        cos_dev = cos_anneal.detach().reshape(1).float().contiguous() if isinstance(cos_anneal, torch.Tensor) else None
+        cos_f = 0.0 if cos_dev is not None else float(cos_anneal)
+        n_dev = rsp.cur_nr_samples if RaySamplesPacked.static_capacity else None
+        call("psdf_neus_render_loss_forward", *rsp._rsp(), sdf_c, grad_c, rgb_c, rsp.samples_dirs, rsp.samples_dt, inv_s_c, cos_f, cos_dev,
              gt_rgb, gt_mask, hit, bg_c, alpha, T, w, pred, wsum, bgT, ray_loss)
-        scales = torch.tensor([1.0 / (3 * R), (w_mask / R) if gt_mask is not None else 0.0, w_eik / max(N, 1)], device=dev)
         terms = ray_loss.sum(0)
-        loss = (terms * scales).sum()
+        c_rgb, c_mask = 1.0 / (3 * R), (w_mask / R) if gt_mask is not None else 0.0
+        if n_dev is None:
+            c_eik = w_eik / max(N, 1)
+            loss = terms[0] * c_rgb + terms[1] * c_mask + terms[2] * c_eik
+        else:
+            c_eik = w_eik           # divided by the device-side sample count
+            loss = terms[0] * c_rgb + terms[1] * c_mask + terms[2] * (w_eik / n_dev.clamp(min=1).float()).squeeze(0)
         ctx.rsp = rsp
-        ctx.cfg = (float(cos_anneal), gt_rgb, gt_mask, hit, 1.0 / (3 * R), (w_mask / R) if gt_mask is not None else 0.0, w_eik / max(N, 1))
+        ctx.cfg = (cos_f, cos_dev, gt_rgb, gt_mask, hit, c_rgb, c_mask, c_eik, n_dev)
         ctx.has_bg = bg_rgb is not None
         ctx.save_for_backward(sdf_c, grad_c, rgb_c, inv_s_c, bg_c, alpha, T, pred, wsum, bgT)
         ctx.mark_non_differentiable(pred, wsum, w, terms)
@@ -154,14 +170,16 @@ class _NeusRenderLossFn(torch.autograd.Function):
     def backward(ctx, g_loss, *_):
         sdf, grad, rgb, inv_s, bg, alpha, T, pred, wsum, bgT = ctx.saved_tensors
         rsp = ctx.rsp
-        cos_anneal, gt_rgb, gt_mask, hit, s_rgb, s_mask, s_eik = ctx.cfg
-        g_sdf = torch.empty_like(sdf)
-        g_grad = torch.empty_like(grad)
-        g_rgb = torch.empty_like(rgb)
+        cos_f, cos_dev, gt_rgb, gt_mask, hit, s_rgb, s_mask, s_eik, n_dev = ctx.cfg
+        # rows outside every ray (gaps of slot-strided containers, the zero tail of static-capacity ones) get no gradient
+        g_sdf = torch.zeros_like(sdf)
+        g_grad = torch.zeros_like(grad)
+        g_rgb = torch.zeros_like(rgb)
         g_bg = torch.empty_like(bg) if ctx.has_bg and ctx.needs_input_grad[5] else None
         g_inv = torch.zeros(1, device=sdf.device) if ctx.needs_input_grad[4] else None
-        call("psdf_neus_render_loss_backward", *rsp._rsp(), sdf, grad, rgb, rsp.samples_dirs, rsp.samples_dt, inv_s, cos_anneal, gt_rgb, gt_mask,
-             hit, bg, alpha, T, pred, wsum, bgT, g_loss.reshape(1).contiguous(), s_rgb, s_mask, s_eik, g_sdf, g_grad, g_rgb, g_bg, g_inv)
+        call("psdf_neus_render_loss_backward", *rsp._rsp(), sdf, grad, rgb, rsp.samples_dirs, rsp.samples_dt, inv_s, cos_f, cos_dev, gt_rgb,
+             gt_mask, hit, bg, alpha, T, pred, wsum, bgT, g_loss.reshape(1).contiguous(), s_rgb, s_mask, s_eik, n_dev, g_sdf, g_grad, g_rgb,
+             g_bg, g_inv)
         ctx.rsp = None
         return (None, g_sdf, g_grad, g_rgb, None if g_inv is None else g_inv.reshape(()), g_bg, None, None, None, None, None, None)
 

@@ -18,8 +18,59 @@ from .permuto_sdf import PermutoSDF, RaySamplesPacked
 from .volume_rendering import VolumeRenderingNerf, VolumeRenderingNeus
 
 
+class DeviceIter:
+    """Iteration number held twice: `host` (int) drives Python control flow, `dev` (0-d float32 CUDA tensor with the same
+    value) feeds every quantity that changes from one iteration to the next (map_range_val ramps). A training iteration
+    captured in a CUDA graph with a DeviceIter stays valid while lo <= iteration < hi: every comparison against the
+    iteration narrows [lo, hi) to the range over which the branch that was taken does not change."""
+
+    def __init__(self, host, dev):
+        self.host, self.dev = int(host), dev
+        self.lo, self.hi = float("-inf"), float("inf")
+
+    def __int__(self):
+        return self.host
+
+    __index__ = __int__
+
+    def __float__(self):
+        return float(self.host)
+
+    def _at_least(self, bound):
+        if self.host >= bound:
+            self.lo = max(self.lo, bound)
+            return True
+        self.hi = min(self.hi, bound)
+        return False
+
+    def __ge__(self, o):
+        return self._at_least(math.ceil(o))
+
+    def __lt__(self, o):
+        return not self._at_least(math.ceil(o))
+
+    def __gt__(self, o):
+        return self._at_least(math.floor(o) + 1)
+
+    def __le__(self, o):
+        return not self._at_least(math.floor(o) + 1)
+
+    def __eq__(self, o):
+        raise TypeError("DeviceIter: equality tests are not replayable; compare with <, <=, >, >=")
+
+    __hash__ = None
+
+
 def map_range_val(input_val, input_start, input_end, output_start, output_end):
-    """common_utils.py:156-160 (clamps its input)"""
+    """common_utils.py:156-160 (clamps its input). For a DeviceIter the plateaus return Python floats (and narrow its validity
+    range), the ramp returns a 0-d device tensor computed from the device-resident iteration."""
+    if isinstance(input_val, DeviceIter):
+        if input_val <= input_start:
+            return output_start
+        if input_val >= input_end:
+            return output_end
+        x = torch.clamp(input_val.dev, input_start, input_end)
+        return output_start + ((output_end - output_start) / (input_end - input_start)) * (x - input_start)
     c = max(input_start, min(input_end, input_val))
     return output_start + ((output_end - output_start) / (input_end - input_start)) * (c - input_start)
 
@@ -131,7 +182,7 @@ class SDF(torch.nn.Module):
 
     def forward(self, points, iter_nr):
         assert points.shape[1] == self.in_channels, "points should be N x in_channels"
-        self.last_iter_nr = iter_nr
+        self.last_iter_nr = int(iter_nr)
         if getattr(self, "fused", None) is not None and not torch.is_grad_enabled():
             sdf, _, geom = self.fused(points, iter_nr, with_gradient=False, with_geom=self.geom_feat_size_out != 0)
             return sdf, geom
@@ -197,7 +248,7 @@ class RGB(torch.nn.Module):
     def forward(self, points, samples_dirs, sdf_gradients, geom_feat, iter_nr, model_colorcal=None, img_indices=None,
                 ray_start_end_idx=None):
         assert points.shape[1] == self.in_channels, "points should be N x in_channels"
-        self.last_iter_nr = iter_nr
+        self.last_iter_nr = int(iter_nr)
         window = self.c2f(map_range_val(iter_nr, 0.0, self.nr_iters_for_c2f, 0.3, 1.0))
         feat = self.encoding(points, window.view(-1))
         with torch.no_grad():
@@ -239,7 +290,7 @@ class NerfHash(torch.nn.Module):
 
     def forward(self, samples_pos, samples_dirs, iter_nr, model_colorcal=None, img_indices=None, ray_start_end_idx=None):
         assert samples_pos.shape[1] == self.in_channels
-        self.last_iter_nr = iter_nr
+        self.last_iter_nr = int(iter_nr)
         window = self.c2f(map_range_val(iter_nr, 0.0, self.nr_iters_for_c2f, 0.3, 1.0))
         feat = self.encoding(samples_pos, window.view(-1))
         with torch.no_grad():

@@ -28,6 +28,8 @@ class FusedAdamW:
         self.exp_avg = torch.zeros(total, device=dev)
         self.exp_avg_sq = torch.zeros(total, device=dev)
         self.step_count = 0
+        self.device_step = False        # True: the step count is kept in self.step_dev (device) for CUDA-graph replay
+        self.step_dev = None
         for g, (ps, off, n, n_pad) in zip(groups, layout):
             o = off
             for p in ps:
@@ -48,12 +50,18 @@ class FusedAdamW:
     def step(self, grad_scale=1.0):
         self.step_count += 1
         b1, b2 = self.betas
+        step_dev = None
+        if self.device_step:            # CUDA-graph mode: the step counter lives (and is incremented) on the device
+            if self.step_dev is None:
+                self.step_dev = torch.full((1,), self.step_count - 1, dtype=torch.int32, device=self.flat_param.device)
+            self.step_dev.add_(1)
+            step_dev = self.step_dev
         for g in self.param_groups:
             off, n = g["_off"], g["_n"]
             if n == 0:
                 continue
             call("psdf_adamw_step", n, self.flat_param[off:off + n], self.flat_grad[off:off + n], self.exp_avg[off:off + n],
-                 self.exp_avg_sq[off:off + n], float(g["lr"]), b1, b2, self.eps, float(g["weight_decay"]), self.step_count,
+                 self.exp_avg_sq[off:off + n], float(g["lr"]), b1, b2, self.eps, float(g["weight_decay"]), self.step_count, step_dev,
                  float(grad_scale), 1)
 
     def state_dict(self):

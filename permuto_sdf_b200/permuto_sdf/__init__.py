@@ -27,8 +27,32 @@ class _Pcg32Host:
     def __init__(self):
         self.state = 0x853C49E6748FEA9B
         self.inc = 0xDA3E39CB94B95BDB
+        self.dev = None          # device-resident {state, inc} (int64 bit patterns) while CUDA-graph replay owns the stream
+
+    def args(self):
+        """(rng_state, rng_inc) of a C-ABI call: by value, or (device pointer, 0) for a device-resident generator"""
+        if self.dev is not None:
+            return self.dev.data_ptr(), 0
+        return self.state, self.inc
+
+    def to_device(self):
+        """move the generator into device memory (kernels read it there; replayable from a CUDA graph)"""
+        if self.dev is None:
+            sg = lambda v: v - (1 << 64) if v >= (1 << 63) else v
+            self.dev = torch.tensor([sg(self.state), sg(self.inc)], dtype=torch.int64, device=_dev())
+        return self.dev
+
+    def to_host(self):
+        """bring a device-resident generator back (host sync)"""
+        if self.dev is not None:
+            st = self.dev.cpu().tolist()
+            self.state, self.inc = st[0] & _MASK64, st[1] & _MASK64
+            self.dev = None
 
     def advance(self, delta=1 << 32):
+        if self.dev is not None:
+            call("psdf_rng_advance_dev", self.dev, int(delta))
+            return
         cur_mult, cur_plus, acc_mult, acc_plus = _PCG_MULT, self.inc, 1, 0
         delta &= _MASK64
         while delta > 0:
@@ -55,18 +79,26 @@ def _f32(t, name, cols=None):
 
 # ======================================================================================================
 class RaySamplesPacked:
-    """include/permuto_sdf/RaySamplesPacked.cuh:7-46, src/RaySamplesPacked.cu:19-155"""
+    """include/permuto_sdf/RaySamplesPacked.cuh:7-46, src/RaySamplesPacked.cu:19-155
 
-    def __init__(self, nr_rays, nr_samples_maximum):
+    `RaySamplesPacked.static_capacity = True` switches compaction to a sync-free mode: compact_to_valid_samples keeps the
+    capacity of its input (valid samples packed at the front, zero-filled tail, exact count only in the device tensor
+    cur_nr_samples), so that every tensor shape of an iteration is known on the host and the iteration can be captured in a
+    CUDA graph. The default (False) sizes the compacted container exactly, with the reference's host sync."""
+    static_capacity = False
+
+    def __init__(self, nr_rays, nr_samples_maximum, zero=False):
         d = _dev()
         self.m_nr_rays = int(nr_rays)
         self.max_nr_samples = int(nr_samples_maximum)
         M = self.max_nr_samples
+        alloc = torch.zeros if zero else torch.empty
+        self.is_compact = False
         self.cur_nr_samples = torch.zeros(1, dtype=torch.int32, device=d)
-        self.samples_pos = torch.empty(M, 3, device=d)
-        self.samples_dirs = torch.empty(M, 3, device=d)
-        self.samples_z = torch.empty(M, 1, device=d)
-        self.samples_dt = torch.empty(M, 1, device=d)
+        self.samples_pos = alloc(M, 3, device=d)
+        self.samples_dirs = alloc(M, 3, device=d)
+        self.samples_z = alloc(M, 1, device=d)
+        self.samples_dt = alloc(M, 1, device=d)
         self._samples_pos_4d = None   # allocated on first use (only background containers need it)
         self._samples_sdf = None
         self.ray_fixed_dt = torch.empty(self.m_nr_rays, 1, device=d)
@@ -104,19 +136,31 @@ class RaySamplesPacked:
     def compact_to_valid_samples(self):
         R = self.m_nr_rays
         d = self.ray_start_end_idx.device
+        static = RaySamplesPacked.static_capacity
+        if static and self.is_compact:
+            return self
         nblocks = (max(R, 1) + 1023) // 1024
         ws = torch.empty(R + nblocks + 1, dtype=torch.int32, device=d)
         se = self.ray_start_end_idx.contiguous()
         if R > 0:
             call("psdf_packed_compact_scan", R, se, ws)
-            exact = int(ws[R + nblocks].item())  # same host sync as the reference (RaySamplesPacked.cu:51)
+            # exact size: the reference's host sync (RaySamplesPacked.cu:51); static mode keeps the capacity instead
+            exact = self.max_nr_samples if static else int(ws[R + nblocks].item())
         else:
             exact = 0
-        out = RaySamplesPacked(R, exact)
+        out = RaySamplesPacked(R, exact, zero=static)
+        out.is_compact = True
         out.has_sdf = self.has_sdf
         out.rays_have_equal_nr_of_samples = self.rays_have_equal_nr_of_samples
         out.fixed_nr_of_samples_per_ray = self.fixed_nr_of_samples_per_ray
-        out.cur_nr_samples.fill_(exact)
+        if static and R > 0:
+            out.cur_nr_samples = ws[R + nblocks:R + nblocks + 1]
+            if self._samples_pos_4d is not None:
+                out._samples_pos_4d = torch.zeros(exact, 4, device=d)
+            if self._samples_sdf is not None:
+                out._samples_sdf = torch.zeros(exact, 1, device=d)
+        else:
+            out.cur_nr_samples.fill_(exact)
         if R > 0:
             pos4 = self._samples_pos_4d
             sdf = self._samples_sdf if self._samples_sdf is not None else None
@@ -153,7 +197,8 @@ class RaySamplesPacked:
     @staticmethod
     def compute_per_sample_ray_idx(ray_start_end_idx, nr_samples):
         R = ray_start_end_idx.shape[0]
-        out = torch.empty(int(nr_samples), dtype=torch.int32, device=ray_start_end_idx.device)
+        # rows outside every ray keep index 0 (a valid row for downstream gathers)
+        out = torch.zeros(int(nr_samples), dtype=torch.int32, device=ray_start_end_idx.device)
         call("psdf_packed_per_sample_ray_idx", R, int(nr_samples), ray_start_end_idx.contiguous(), out)
         return out
 
@@ -254,7 +299,7 @@ class OccupancyGrid:
         n = self.get_nr_voxels()
         out = torch.empty(n, 3, device=self.m_grid_values.device)
         V, e, t = self._geom()
-        call("psdf_occ_compute_grid_points", n, V, e, t, None, OccupancyGrid.m_rng.state, OccupancyGrid.m_rng.inc,
+        call("psdf_occ_compute_grid_points", n, V, e, t, None, *OccupancyGrid.m_rng.args(),
              1 if randomize_position else 0, out)
         if randomize_position:
             OccupancyGrid.m_rng.advance()
@@ -266,7 +311,7 @@ class OccupancyGrid:
         out = torch.empty(n, 3, device=d)
         idx = torch.randint(0, self.get_nr_voxels(), (n,), dtype=torch.int32, device=d)
         V, e, t = self._geom()
-        call("psdf_occ_compute_grid_points", n, V, e, t, idx, OccupancyGrid.m_rng.state, OccupancyGrid.m_rng.inc,
+        call("psdf_occ_compute_grid_points", n, V, e, t, idx, *OccupancyGrid.m_rng.args(),
              1 if randomize_position else 0, out)
         if randomize_position:
             OccupancyGrid.m_rng.advance()
@@ -320,7 +365,7 @@ class OccupancyGrid:
         V, e, t = self._geom()
         call("psdf_occ_compute_samples_in_occupied_regions", R, V, e, t, o, dr, _f32(ray_t_entry, "t_entry"),
              _f32(ray_t_exit, "t_exit"), self.m_grid_occupancy, float(min_dist_between_samples), int(max_nr_samples_per_ray), M,
-             OccupancyGrid.m_rng.state, OccupancyGrid.m_rng.inc, 1 if jitter_samples else 0, 1, rsp.samples_pos,
+             *OccupancyGrid.m_rng.args(), 1 if jitter_samples else 0, 1, rsp.samples_pos,
              rsp.samples_dirs, rsp.samples_z, rsp.samples_dt, rsp.ray_fixed_dt, rsp.ray_start_end_idx, rsp.cur_nr_samples)
         if jitter_samples:
             OccupancyGrid.m_rng.advance()
@@ -365,8 +410,7 @@ class RaySampler:
         rsp.rays_have_equal_nr_of_samples = True
         rsp.fixed_nr_of_samples_per_ray = n
         c = sphere_center.tolist() if isinstance(sphere_center, torch.Tensor) else list(sphere_center)
-        call("psdf_sampler_bg", R, n, o, dr, _f32(ray_t_exit, "ray_t_exit"), float(sphere_radius), c, RaySampler.m_rng.state,
-             RaySampler.m_rng.inc, 1 if randomize_position else 0, 1 if contract_3d_samples else 0, rsp.samples_pos,
+        call("psdf_sampler_bg", R, n, o, dr, _f32(ray_t_exit, "ray_t_exit"), float(sphere_radius), c, *RaySampler.m_rng.args(), 1 if randomize_position else 0, 1 if contract_3d_samples else 0, rsp.samples_pos,
              rsp.samples_pos_4d, rsp.samples_dirs, rsp.samples_z, rsp.samples_dt, rsp.ray_fixed_dt, rsp.ray_start_end_idx)
         if randomize_position:
             RaySampler.m_rng.advance()
@@ -381,7 +425,7 @@ class RaySampler:
         M = max(R * int(max_nr_samples_per_ray), 1)
         rsp = RaySamplesPacked(R, M)
         call("psdf_sampler_fg", R, o, dr, _f32(ray_t_entry, "t_entry"), _f32(ray_t_exit, "t_exit"),
-             float(min_dist_between_samples), int(max_nr_samples_per_ray), M, RaySampler.m_rng.state, RaySampler.m_rng.inc,
+             float(min_dist_between_samples), int(max_nr_samples_per_ray), M, *RaySampler.m_rng.args(),
              1 if randomize_position else 0, 1, rsp.samples_pos, rsp.samples_dirs, rsp.samples_z, rsp.samples_dt,
              rsp.ray_fixed_dt, rsp.ray_start_end_idx, rsp.cur_nr_samples)
         if randomize_position:
@@ -468,8 +512,7 @@ class VolumeRendering:
         imp.rays_have_equal_nr_of_samples = True
         imp.fixed_nr_of_samples_per_ray = k
         call("psdf_vr_importance_sample", *rsp._rsp(), _f32(ray_origins, "ray_origins", 3), _f32(ray_dirs, "ray_dirs", 3),
-             rsp.ray_fixed_dt, rsp.samples_z, _f32(sample_cdf, "cdf", 1), k, VolumeRendering.m_rng.state,
-             VolumeRendering.m_rng.inc, 1 if jitter_samples else 0, imp.samples_pos, imp.samples_dirs, imp.samples_z)
+             rsp.ray_fixed_dt, rsp.samples_z, _f32(sample_cdf, "cdf", 1), k, *VolumeRendering.m_rng.args(), 1 if jitter_samples else 0, imp.samples_pos, imp.samples_dirs, imp.samples_z)
         if jitter_samples:
             VolumeRendering.m_rng.advance()
         return imp
@@ -483,7 +526,10 @@ class VolumeRendering:
         R = rsp.ray_start_end_idx.shape[0]
         k = rsp_imp.fixed_nr_of_samples_per_ray
         c_max = VolumeRendering._N(rsp) + R * k
-        comb = RaySamplesPacked(R, max(c_max, 1))
+        comb = RaySamplesPacked(R, max(c_max, 1), zero=RaySamplesPacked.static_capacity)
+        comb.is_compact = True          # the merge writes ray after ray at the scanned offsets
+        if RaySamplesPacked.static_capacity and rsp.has_sdf:
+            comb._samples_sdf = torch.zeros(max(c_max, 1), 1, device=rsp.samples_z.device)
         comb.has_sdf = rsp.has_sdf
         nblocks = (max(R, 1) + 1023) // 1024
         ws = torch.empty(R + nblocks + 1, dtype=torch.int32, device=rsp.samples_z.device)

@@ -153,11 +153,17 @@ class Coarse2Fine(torch.nn.Module):
         super().__init__()
         self.nr_levels = int(nr_levels)
         self.last_t = 0
+        self._cache = None
 
     def forward(self, t):
         self.last_t = t
         dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
-        return cosine_easing_window(self.nr_levels, float(t) * self.nr_levels, device=dev)
+        if isinstance(t, torch.Tensor):          # device-resident schedule (CUDA-graph replay): no host read
+            return cosine_easing_window(self.nr_levels, t * float(self.nr_levels), device=t.device)
+        key = (float(t), str(dev))
+        if self._cache is None or self._cache[0] != key:     # plateaus of the schedule: nothing to recompute
+            self._cache = (key, cosine_easing_window(self.nr_levels, float(t) * self.nr_levels, device=dev))
+        return self._cache[1]
 
     def get_last_t(self):
         return self.last_t

@@ -14,7 +14,7 @@ import math
 import torch
 import torch.nn.functional as F
 
-from .models import RGB, SDF, Colorcal, NerfHash, map_range_val
+from .models import RGB, SDF, Colorcal, DeviceIter, NerfHash, map_range_val
 from .permuto_sdf import OccupancyGrid, PermutoSDF, RaySampler, RaySamplesPacked, Sphere, VolumeRendering
 
 
@@ -265,6 +265,7 @@ class Trainer:
         else:
             self.optimizer = torch.optim.AdamW(groups, amsgrad=False, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, lr=hp.lr)
         self.iter_nr = 0
+        self._cg = None                 # CUDA-graph state (enable_cuda_graph)
         self.nr_rays_to_create = hp.nr_rays
         self.last = {}
 
@@ -291,7 +292,7 @@ class Trainer:
         fused_done = fl is not None and fl["loss"] is not None
         if fused_done:
             loss = fl["loss"]      # rgb L1 + eikonal + mask terms, already weighted
-            nr = max(fg.samples_pos.shape[0], 1)
+            nr = fg.cur_nr_samples.clamp(min=1).float().squeeze(0) if RaySamplesPacked.static_capacity else max(fg.samples_pos.shape[0], 1)
             loss_rgb, loss_eik = fl["terms"][0] / (3.0 * ray_origins.shape[0]), fl["terms"][2] / nr
         else:
             loss_rgb = rgb_loss(gt_rgb, pred_rgb, does_hit)
@@ -300,10 +301,15 @@ class Trainer:
             loss = loss + loss_eik * hp.eikonal_weight
         gw_curv = map_range_val(iter_nr_for_anneal, hp.iter_start_reduce_curv, hp.iter_finish_reduce_curv, 1.0, 0.0)
         loss_curv = torch.zeros((), device=loss.device)
-        if gw_curv > 0.0 and fg.samples_pos.shape[0] != 0:
+        if iter_nr_for_anneal < hp.iter_finish_reduce_curv and fg.samples_pos.shape[0] != 0:      # <=> gw_curv > 0
             _, curv = self.model_sdf.get_sdf_and_curvature_1d_precomputed_gradient_normal_based(fg.samples_pos, sdf_gradients,
                                                                                                 iter_nr_for_anneal)
-            loss_curv = curv.mean()
+            if RaySamplesPacked.static_capacity:     # rows past the device-side sample count are padding
+                n_dev = fg.cur_nr_samples
+                valid = (torch.arange(curv.shape[0], device=curv.device, dtype=torch.int32) < n_dev).view(-1, 1)
+                loss_curv = torch.where(valid, curv, torch.zeros_like(curv)).sum() / n_dev.clamp(min=1).float().squeeze(0)
+            else:
+                loss_curv = curv.mean()
             loss = loss + loss_curv * hp.curvature_weight * gw_curv
         if hp.use_occupancy_grid:
             off = self.aabb.rand_points_inside(nr_points=1024)
@@ -315,7 +321,7 @@ class Trainer:
         if hp.with_mask and not fused_done:
             loss = loss + F.binary_cross_entropy(weights_sum.clip(1e-3, 1.0 - 1e-3), gt_mask) * hp.mask_weight
         self.last = dict(loss_rgb=loss_rgb.detach(), loss_eikonal=loss_eik.detach(), loss_curvature=loss_curv.detach(),
-                         nr_samples=fg.samples_pos.shape[0], fg=fg)
+                         nr_samples=fg.samples_pos.shape[0], nr_samples_dev=fg.cur_nr_samples, fg=fg)
         return loss
 
     def update_occupancy(self, iter_nr_for_anneal):
@@ -328,6 +334,8 @@ class Trainer:
     def step(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy=None, optimizer_step=True):
         """forward + losses + backward (+ optimizer). Returns the detached loss tensor (no host sync)."""
         self.model_sdf.train(); self.model_rgb.train()
+        if self._cg is not None:
+            return self._step_graphed(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy, optimizer_step)
         it = self.iter_nr
         loss = self.losses(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, it)
         if update_occupancy is None:
@@ -341,7 +349,138 @@ class Trainer:
         self.iter_nr += 1
         return loss.detach()
 
+    # ------------------------------------------------------------------------------------ CUDA-graph replay
+    def enable_cuda_graph(self, warmup_steps=3):
+        """Run the iteration from CUDA graphs: sync-free static-capacity containers, device-resident pcg32 generators,
+        iteration number and AdamW step count, so that one captured (losses + backward) graph and one (optimizer) graph
+        replay until the Python control flow of the iteration would change (DeviceIter validity range).
+        The first `warmup_steps` iterations run eagerly (on the capture stream) with the same static shapes."""
+        if not hasattr(self.optimizer, "flat_grad"):
+            raise RuntimeError("CUDA-graph mode needs the flat-buffer optimizer (optimizer='fused')")
+        RaySamplesPacked.static_capacity = True
+        for r in (OccupancyGrid.m_rng, RaySampler.m_rng, VolumeRendering.m_rng):
+            r.to_device()
+        opt = self.optimizer
+        opt.device_step = True
+        dev = opt.flat_param.device
+        opt.step_dev = torch.full((1,), opt.step_count, dtype=torch.int32, device=dev)
+        self._cg = dict(warm=int(warmup_steps), fb=None, opt={}, it_dev=torch.zeros((), device=dev), it_host=None,
+                        stream=torch.cuda.Stream(device=dev), launches=0)
+
+    def disable_cuda_graph(self):
+        """back to eager iterations with exactly-sized containers (host sync per compaction, like the reference)"""
+        if self._cg is None:
+            return
+        torch.cuda.synchronize()
+        RaySamplesPacked.static_capacity = False
+        for r in (OccupancyGrid.m_rng, RaySampler.m_rng, VolumeRendering.m_rng):
+            r.to_host()
+        self.optimizer.device_step = False
+        self.optimizer.step_dev = None
+        self._cg = None
+
+    def _sync_device_iter(self):
+        cg = self._cg
+        if cg["it_host"] != self.iter_nr:
+            cg["it_dev"].fill_(float(self.iter_nr))
+            cg["it_host"] = self.iter_nr
+
+    def _step_graphed(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy, optimizer_step):
+        cg = self._cg
+        it = self.iter_nr
+        self._sync_device_iter()
+        inputs = [ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices]
+        shapes = tuple(None if t is None else (tuple(t.shape), t.dtype) for t in inputs)
+        fb = cg["fb"]
+        valid = fb is not None and fb["shapes"] == shapes and fb["lo"] <= it < fb["hi"]
+        cur = torch.cuda.current_stream()
+        if not valid and cg["warm"] > 0:
+            # eager iteration with the static shapes, on the capture stream (lazy library state initialises there)
+            cg["warm"] -= 1
+            side = cg["stream"]
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                loss = self.losses(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, DeviceIter(it, cg["it_dev"]))
+                self.optimizer.zero_grad(set_to_none=False)
+                loss.backward()
+                loss = loss.detach()
+            cur.wait_stream(side)
+        else:
+            if not valid:
+                fb = cg["fb"] = self._capture_forward_backward(inputs, shapes, it)
+            for dst, src in zip(fb["static"], inputs):
+                if dst is not None:
+                    dst.copy_(src, non_blocking=True)
+            fb["graph"].replay()
+            self.last = fb["last"]
+            loss = fb["loss"]
+            for m in (self.model_sdf, self.model_rgb, self.model_bg):
+                if m is not None:
+                    m.last_iter_nr = it
+        if update_occupancy is None:
+            update_occupancy = (it % 8 == 0)
+        if update_occupancy and self.hp.use_occupancy_grid:
+            self.update_occupancy(it)
+        if optimizer_step:
+            self.optimizer_step()
+        self.iter_nr += 1
+        return loss
+
+    def _capture_forward_backward(self, inputs, shapes, it):
+        cg = self._cg
+        static = [None if t is None else t.detach().clone() for t in inputs]
+        dit = DeviceIter(it, cg["it_dev"])
+        self.optimizer.zero_grad(set_to_none=False)
+        torch.cuda.synchronize()
+        from ._lib import stats_begin, stats_end
+        stats_begin(with_events=False)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=cg["stream"]):
+            loss = self.losses(*static, dit)
+            loss.backward()
+            out = loss.detach()
+        _, launches, _ = stats_end()
+        return dict(graph=g, static=static, loss=out, last=self.last, shapes=shapes, lo=dit.lo, hi=dit.hi, launches=launches)
+
+    def _optimizer_step_graphed(self, grad_scale):
+        cg = self._cg
+        if cg["fb"] is None:            # still in the eager warm-up iterations
+            side, cur = cg["stream"], torch.cuda.current_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.optimizer.step(grad_scale=grad_scale)
+                self.model_sdf.fused.repack()
+                cg["it_dev"].add_(1.0)
+            cur.wait_stream(side)
+        else:
+            og = cg["opt"].get(grad_scale)
+            if og is None:
+                from ._lib import stats_begin, stats_end
+                torch.cuda.synchronize()
+                stats_begin(with_events=False)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=cg["stream"]):
+                    self.optimizer.step(grad_scale=grad_scale)
+                    self.model_sdf.fused.repack()
+                    cg["it_dev"].add_(1.0)
+                _, launches, _ = stats_end()
+                self.optimizer.step_count -= 1          # capture records, it does not run
+                og = cg["opt"][grad_scale] = dict(graph=g, launches=launches)
+            og["graph"].replay()
+            self.optimizer.step_count += 1
+        if cg["it_host"] is not None:
+            cg["it_host"] += 1          # the device-resident iteration number was advanced with the optimizer
+
+    def graph_launches_per_step(self):
+        """kernels of this library inside one replayed iteration (counted while capturing)"""
+        cg = self._cg
+        if cg is None or cg["fb"] is None:
+            return None
+        return cg["fb"]["launches"] + sum(o["launches"] for o in cg["opt"].values())
+
     def optimizer_step(self, grad_scale=1.0):
+        if self._cg is not None:
+            return self._optimizer_step_graphed(float(grad_scale))
         if hasattr(self.optimizer, "flat_grad"):
             self.optimizer.step(grad_scale=grad_scale)
             if getattr(self.model_sdf, "fused", None) is not None:

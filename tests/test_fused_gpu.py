@@ -126,3 +126,27 @@ def test_fused_sdf_large_and_ragged(cuda):
         if N:
             s1, g1, f1 = m.get_sdf_and_gradient(pos.clone(), 10)
             assert rel(sdf, s1) < 1e-3 and rel(grad, g1) < 1e-3 and rel(geom, f1) < 1e-3
+
+
+@pytest.mark.parametrize("M,N", [(64, 64), (64, 48), (16, 64), (48, 16)])
+def test_umma_transposed_gemm_weight_gradient_layout(cuda, M, N):
+    """dW-style product D = A^T B with the sample axis as the MMA K dimension (MN-major operands straight from activation tiles).
+    The kernel dumps every TMEM lane; the test also reports where the M = 64 accumulator rows live."""
+    from permuto_sdf_b200._lib import call
+    torch.manual_seed(M * 100 + N)
+    A = torch.randn(128, M, device="cuda")
+    B = torch.randn(128, N, device="cuda")
+    dump = torch.full((128, 64), float("nan"), device="cuda")
+    call("psdf_debug_umma_gemm_tn", M, N, A, B, dump)
+    torch.cuda.synchronize()
+    want = (A.double().t() @ B.double()).float()
+    Mp = (M + 15) // 16 * 16
+    # accumulator row m of an M<=64, cta_group::1 instruction: find the lane that holds it
+    lanes = []
+    for m in range(M):
+        err = (dump[:, :N] - want[m][None, :]).abs().max(dim=1).values
+        lane = int(err.argmin())
+        assert float(err[lane]) < 2e-3 * float(want.abs().max()), "row %d not found in TMEM (best lane %d, err %g)" % (m, lane, float(err[lane]))
+        lanes.append(lane)
+    print("M=%d N=%d accumulator row -> lane:" % (M, N), lanes)
+    assert lanes == list(range(M)) or lanes == [(m // 16) * 32 + (m % 16) for m in range(M)], lanes
