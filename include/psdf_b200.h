@@ -163,6 +163,21 @@ int psdf_neus_render_loss_backward(PSDF_RSP, const float* sdf, const float* grad
                                    const int* nr_samples_dev, float* g_sdf,
                                    float* g_grad, float* g_rgb, float* g_bg_rgb, float* g_inv_s, void* stream);
 
+/* ---------------------------------------------------------------- colour network helpers
+ * LipshitzMLP weight normalisation (permuto_sdf_py/models/models.py:96-110): W_eff[r,:] = W[r,:] * min(1, softplus(c) / sum|W[r,:]|);
+ * W [rows,cols], c [1] device scalar. Backward: grad_W (=), grad_c (+=, may be NULL). */
+int psdf_lipschitz_normalize(int rows, int cols, const float* W, const float* c, float* W_eff, void* stream);
+int psdf_lipschitz_normalize_backward(int rows, int cols, const float* W, const float* c, const float* grad_W_eff, float* grad_W,
+                                      float* grad_c, void* stream);
+/* Colorcal.calib_RGB_samples_packed + sigmoid (models.py:395-414, 677-741) on packed samples: out = sigmoid(x (1 + weight_delta[img]) +
+ * bias[img]), identity calibration for img == fixed_img or img_idx == NULL (img_idx [R] per ray). Rows outside every ray are not
+ * written. Backward: grad_x (=, rows inside rays), grad_weight_delta / grad_bias [nr_imgs,3] (+=, may be NULL). */
+int psdf_calib_sigmoid_forward(PSDF_RSP, const float* x, const int* img_idx, const float* weight_delta, const float* bias, int fixed_img,
+                               float* out, void* stream);
+int psdf_calib_sigmoid_backward(PSDF_RSP, const float* x, const float* out, const float* grad_out, const int* img_idx,
+                                const float* weight_delta, int fixed_img, float* grad_x, float* grad_weight_delta, float* grad_bias,
+                                void* stream);
+
 /* ---------------------------------------------------------------- PermutoSDF statics (include/permuto_sdf/PermutoSDF.cuh:46-55) */
 int psdf_spherical_harmonics(int n, int degree, const float* dirs, float* out, void* stream);
 int psdf_random_rays_from_reel(int nr_rays, int nr_images, int H, int W, const float* rgb_reel, const float* mask_reel,
@@ -199,15 +214,16 @@ int psdf_sdf_mlp_pack(int in_dim, int hidden, int out_dim, const float* W0, cons
 int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
                            const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, float* sdf,
                            float* grad, float* geom, void* stream);
-/* Training backward of psdf_sdf_fused_forward (double backward of encoding + MLP in one tcgen05 kernel):
- * upstream gradients g_sdf [N], g_grad [N,3], g_geom [N,out_dim-1] (any may be NULL) -> grad_lattice (+=), bias gradients
- * gb_l [N_l] (+=) and the spill matrices zcat_l [2N, pad16(N_l)], acat_l [2N, pad16(K_l)] with
- * dW_l = (zcat_l^T @ acat_l)[:N_l, :K_l]. Replaces loss.backward() through SDF.get_sdf_and_gradient (models.py:199-259). */
+/* Training backward of psdf_sdf_fused_forward (double backward of encoding + MLP on the tensor cores, two kernels):
+ * upstream gradients g_sdf [N], g_grad [N,3], g_geom [N,out_dim-1] (any may be NULL) -> grad_lattice (+=), weight gradients
+ * gW_l [N_l, K_l] (+=) and bias gradients gb_l [N_l] (+=). workspace: psdf_sdf_fused_backward_workspace_bytes(N) bytes of
+ * scratch (operand-tile spill between the two kernels). Replaces loss.backward() through SDF.get_sdf_and_gradient
+ * (models.py:199-259). */
+long long psdf_sdf_fused_backward_workspace_bytes(int N);
 int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
                             const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, const float* g_sdf,
-                            const float* g_grad, const float* g_geom, float* grad_lattice, float* zcat0, float* zcat1, float* zcat2,
-                            float* zcat3, float* acat0, float* acat1, float* acat2, float* acat3, float* gb0, float* gb1, float* gb2,
-                            float* gb3, void* stream);
+                            const float* g_grad, const float* g_geom, float* grad_lattice, uint8_t* workspace, float* gW0, float* gW1,
+                            float* gW2, float* gW3, float* gb0, float* gb1, float* gb2, float* gb3, void* stream);
 /* ---------------------------------------------------------------- dense fused AdamW (torch.optim.AdamW / apex FusedAdam math,
  * train_permuto_sdf.py:293-304); step >= 1 is the incremented step count; grad is multiplied by grad_scale and, when
  * zero_grad != 0, reset to zero in the same pass. Pointers 16-byte aligned. step_dev [1] (device int32), when not NULL,

@@ -118,6 +118,18 @@ __device__ __forceinline__ int pos_to_voxel(float px, float py, float pz, const 
     return (int)morton3(__float2uint_rz(x), __float2uint_rz(y), __float2uint_rz(z));
 }
 
+// compile-time choice between the exact reciprocal multiply (power-of-two extent) and the IEEE division, for marching loops
+template <bool kInvMul>
+__device__ __forceinline__ int pos_to_voxel_t(float px, float py, float pz, const GridGeom& g, float Vf) {
+    float qx = __fsub_rn(px, g.tx), qy = __fsub_rn(py, g.ty), qz = __fsub_rn(pz, g.tz);
+    if (kInvMul) { qx = __fmul_rn(qx, g.inv_extent); qy = __fmul_rn(qy, g.inv_extent); qz = __fmul_rn(qz, g.inv_extent); }
+    else { qx = __fdiv_rn(qx, g.extent); qy = __fdiv_rn(qy, g.extent); qz = __fdiv_rn(qz, g.extent); }
+    float x = __fmul_rn(__fadd_rn(qx, 0.5f), Vf);
+    float y = __fmul_rn(__fadd_rn(qy, 0.5f), Vf);
+    float z = __fmul_rn(__fadd_rn(qz, 0.5f), Vf);
+    return (int)morton3(__float2uint_rz(x), __float2uint_rz(y), __float2uint_rz(z));
+}
+
 // voxel index -> centre (or corner) of the voxel in world space (OccupancyGridGPU.cuh:112-155).
 // The reference mixes float and double literals; the float result of each step equals the
 // correctly rounded float op for these constants except the half-voxel shift, which is done in
@@ -160,6 +172,16 @@ __device__ __forceinline__ float dda_step(float px, float py, float pz, float dx
     float t = fminf(fminf(tx, ty), tz);
     return fmaxf(__fmul_rn(t, 1.0f / Vf), 0.0f);   // V is a power of two: t / V == t * (1/V) exactly
 }
+
+// same step with the per-axis half-voxel signs (0.5 sign(d)) hoisted out of the march (they depend on the ray only)
+__device__ __forceinline__ float dda_step_s(float px, float py, float pz, float sx, float sy, float sz, float ix, float iy, float iz,
+                                            float Vf, float inv_V) {
+    float tx = fabsf(__fmul_rn(__fmaf_rn(-px, Vf, floorf(__fadd_rn(__fmaf_rn(px, Vf, 0.5f), sx))), ix));
+    float ty = fabsf(__fmul_rn(__fmaf_rn(-py, Vf, floorf(__fadd_rn(__fmaf_rn(py, Vf, 0.5f), sy))), iy));
+    float tz = fabsf(__fmul_rn(__fmaf_rn(-pz, Vf, floorf(__fadd_rn(__fmaf_rn(pz, Vf, 0.5f), sz))), iz));
+    return fmaxf(__fmul_rn(fminf(fminf(tx, ty), tz), inv_V), 0.0f);
+}
+__device__ __forceinline__ float half_sign(float d) { return d > 0.0f ? 0.5f : (d < 0.0f ? -0.5f : 0.0f); }
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fmaxf(lo, fminf(x, hi)); }
 

@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kTile) k_debug_gemm_tn(int M, int N, const flo
     __syncthreads();
     if (tid == 0) {
         umma::fence_after_sync();
-        const int Mp = pad16(M), Np = pad16(N);
+        const int Mp = 64, Np = pad16(N);      // cta_group::1 accepts M = 64 or 128 only; columns past M are zero
         const uint32_t idesc = umma::make_idesc_mn(Mp, Np, umma::kFmtBF16);
         const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo), bh = umma::smem_u32(b_hi), bl = umma::smem_u32(b_lo);
         for (int kk = 0; kk < kTile / 16; kk++) {

@@ -38,9 +38,10 @@ constexpr unsigned kFull = 0xffffffffu;
 constexpr int kBwdThreads = 512;
 constexpr int kGroups = kBwdThreads / kTile;
 
+constexpr int kSpillTileBytes = 4 * kATileBytes;     // one 128-sample operand tile set: [value hi | value lo | tangent hi | tangent lo]
 struct Spill {
-    float* zcat[kNL];   // [2N, Np_l]   rows [0,N): zbar_l, rows [N,2N): tzbar_l
-    float* acat[kNL];   // [2N, Kp_l]   rows [0,N): a_{l-1}, rows [N,2N): ta_{l-1}
+    uint8_t* zt[kNL];   // [ntiles][64 KB]  zbar_l / tzbar_l operand tiles exactly as they sit in shared memory
+    uint8_t* at[kNL];   // [ntiles][64 KB]  a_{l-1} / ta_{l-1} operand tiles
     float* gbias[kNL];  // [Np_l]  (+=)
 };
 
@@ -79,11 +80,6 @@ __device__ __forceinline__ float colsum16(const float* v, int lane, int& col) {
     d += __shfl_xor_sync(kFull, d, 1);
     col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
     return d;
-}
-// 8 consecutive fp32 of a row to global (two float4 stores)
-__device__ __forceinline__ void st8(float* dst, const float* v) {
-    reinterpret_cast<float4*>(dst)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(dst)[1] = make_float4(v[4], v[5], v[6], v[7]);
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
@@ -127,7 +123,6 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_work = tmem_base + 384;            // 2 x 64 working columns after the 6 x 64 stored ones
     uint32_t w_phase = 0, mma_phase = 0;
-    const size_t Nn = (size_t)P.N;
 
     const int ntiles = (P.N + kTile - 1) / kTile;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -189,10 +184,6 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
             }
             store8(s_a0, s_a0 + kATileBytes, row, kc, fv);
             store8(s_a0 + 2 * kATileBytes, s_a0 + 3 * kATileBytes, row, kc, ft);
-            if (valid) {
-                st8(sp.acat[0] + (size_t)n * K0 + kc * 8, fv);
-                st8(sp.acat[0] + (Nn + n) * K0 + kc * 8, ft);
-            }
         }
         umma::mbar_wait(&bars[0], w_phase);
         w_phase ^= 1;
@@ -206,9 +197,13 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
             const uint8_t* at = (l == 0) ? s_a0 : s_t;
             if (tid == 0) {
                 umma::fence_after_sync();
+                // the input tiles of layer l+1 (a_l, ta_l) go to the weight-gradient spill as they are (TMA store)
+                umma::bulk_s2g(sp.at[l] + (size_t)tile * kSpillTileBytes, at, kSpillTileBytes);
+                umma::bulk_commit();
                 for (int s = 0; s < 2; s++)
                     issue_gemm(tmem_base + (2 * l + s) * 64, at + s * 2 * kATileBytes, at + s * 2 * kATileBytes + kATileBytes, s_w + P.g.w_hi[l],
                                s_w + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
+                umma::bulk_wait_read0();      // before the commit: whoever sees the MMAs done may overwrite the tiles
                 umma::commit(&bars[1]);
             }
             umma::mbar_wait(&bars[1], mma_phase);
@@ -232,11 +227,6 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                     store8(s_t, s_t + kATileBytes, row, 2 * c + 1, z + 8);
                     store8(s_t + 2 * kATileBytes, s_t + 3 * kATileBytes, row, 2 * c, tz);
                     store8(s_t + 2 * kATileBytes, s_t + 3 * kATileBytes, row, 2 * c + 1, tz + 8);
-                    if (valid) {
-                        const int Kn = P.g.Kp[l + 1];
-                        st8(sp.acat[l + 1] + (size_t)n * Kn + c * 16, z); st8(sp.acat[l + 1] + (size_t)n * Kn + c * 16 + 8, z + 8);
-                        st8(sp.acat[l + 1] + (Nn + n) * Kn + c * 16, tz); st8(sp.acat[l + 1] + (Nn + n) * Kn + c * 16 + 8, tz + 8);
-                    }
                 }
             }
             mma_phase ^= 1;
@@ -244,10 +234,17 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
         // all forward MMAs are complete (last commit was waited for): swap in the transposed weights
         umma::fence_before_sync();
         __syncthreads();
+        umma::fence_async_smem();
+        __syncthreads();
         if (tid == 0) {
             umma::mbar_expect_tx(&bars[0], (uint32_t)P.g.total_t);
             umma::bulk_g2s(s_w, blob + P.g.total, (uint32_t)P.g.total_t, &bars[0]);
+            // a_3 / ta_3 (input of the last layer) are only needed for dW_3: spill them before the seed overwrites the tiles
+            umma::bulk_s2g(sp.at[3] + (size_t)tile * kSpillTileBytes, s_t, kSpillTileBytes);
+            umma::bulk_commit();
+            umma::bulk_wait_read0();
         }
+        __syncthreads();
 
         // ---------------- 3. reverse sweep, layers 4..1 (index l = 3..0)
         // seed: zbar_4 = [g_sdf, g_geom...], tzbar_4 = e_0 ; written straight into the working tiles + spill
@@ -268,7 +265,6 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                 }
                 store8(s_t, s_t + kATileBytes, row, c, zb);
                 store8(s_t + 2 * kATileBytes, s_t + 3 * kATileBytes, row, c, tb);
-                if (valid) { st8(sp.zcat[3] + (size_t)n * Np + c * 8, zb); st8(sp.zcat[3] + (Nn + n) * Np + c * 8, tb); }
                 {                                                  // bias gradient: column sums over the warp's 32 rows
                     float z16[16];
 #pragma unroll
@@ -289,9 +285,12 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
             __syncthreads();
             if (tid == 0) {
                 umma::fence_after_sync();
+                umma::bulk_s2g(sp.zt[l] + (size_t)tile * kSpillTileBytes, s_t, kSpillTileBytes);     // zbar_l, tzbar_l tiles
+                umma::bulk_commit();
                 for (int s = 0; s < 2; s++)
                     issue_gemm(tmem_work + s * 64, s_t + s * 2 * kATileBytes, s_t + s * 2 * kATileBytes + kATileBytes, s_w + P.g.t_hi[l],
                                s_w + P.g.t_lo[l], P.g.Np[l], P.g.Kp[l]);
+                umma::bulk_wait_read0();
                 umma::commit(&bars[1]);
             }
             umma::mbar_wait(&bars[1], mma_phase);
@@ -324,10 +323,6 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                         store8(s_t, s_t + kATileBytes, row, 2 * c + 1, ab + 8);
                         store8(s_t + 2 * kATileBytes, s_t + 3 * kATileBytes, row, 2 * c, tab_);
                         store8(s_t + 2 * kATileBytes, s_t + 3 * kATileBytes, row, 2 * c + 1, tab_ + 8);
-                        if (valid) {
-                            st8(sp.zcat[l - 1] + (size_t)n * Kp + c * 16, ab); st8(sp.zcat[l - 1] + (size_t)n * Kp + c * 16 + 8, ab + 8);
-                            st8(sp.zcat[l - 1] + (Nn + n) * Kp + c * 16, tab_); st8(sp.zcat[l - 1] + (Nn + n) * Kp + c * 16 + 8, tab_ + 8);
-                        }
                         {                                              // bias gradient: column sums over the warp's 32 rows
                             if (!valid) {
 #pragma unroll
@@ -393,7 +388,101 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
         int l = i >> 6, c = i & 63;
         if (c < P.g.N[l] && s_gb[i] != 0.0f) atomicAdd(sp.gbias[l] + c, s_gb[i]);
     }
+    if (tid == 0) umma::bulk_wait0();      // spill stores complete before the CTA retires
     if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ weight gradients
+// dW_l [N_l, K_l] = sum over samples of  zbar_l^T a_{l-1} + tzbar_l^T ta_{l-1}  from the spilled operand tiles.
+// The sample axis is the MMA K dimension: a [128 samples x 64 columns] tile in the K-major core-matrix layout used for the
+// forward GEMMs IS an MN-major operand for this product (core matrix = 8 samples x 8 columns; LBO = the 8-sample-group stride,
+// SBO = the 8-column-core stride), so the tiles are multiplied exactly as they were stored: no transposition, no conversion.
+// Persistent CTAs; per (tile, layer, stream) one 64 KB stage = {zbar hi, lo, a hi, lo} arrives by TMA into a 3-deep ring,
+// one thread issues 3 split products x 8 K-steps of tcgen05.mma M64 x N(Kp_l) x K16 accumulating in TMEM (4 layers x 64
+// columns; accumulator row m lives in lane (m / 16) * 32 + m % 16), the epilogue adds the CTA's partial sums to dW (red.add).
+constexpr int kDwStages = 3;
+constexpr int kDwStageBytes = 4 * kATileBytes;
+__global__ void __launch_bounds__(128, 1) k_sdf_dw(MlpGeom g, int ntiles, Spill sp, float* __restrict__ gW0, float* __restrict__ gW1,
+                                                  float* __restrict__ gW2, float* __restrict__ gW3) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* ring = smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kDwStages * kDwStageBytes);
+    uint64_t* empty = full + kDwStages;
+    uint64_t* done = empty + kDwStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int i = 0; i < kDwStages; i++) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
+        umma::mbar_init(done, 1);
+        umma::mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 256);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    int my_tiles = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) my_tiles++;
+    const int nstage = my_tiles * kNL * 2;            // (tile, layer, stream)
+    if (warp == 0 && lane == 0) {
+        // ---- producer: TMA loads
+        for (int i = 0; i < nstage; i++) {
+            const int slot = i % kDwStages, use = i / kDwStages;
+            if (use > 0) umma::mbar_wait(&empty[slot], (use - 1) & 1);
+            const int ti = blockIdx.x + (i / (kNL * 2)) * gridDim.x, l = (i >> 1) % kNL, st = i & 1;
+            uint8_t* dst = ring + slot * kDwStageBytes;
+            umma::mbar_expect_tx(&full[slot], (uint32_t)kDwStageBytes);
+            umma::bulk_g2s(dst, sp.zt[l] + (size_t)ti * kSpillTileBytes + st * 2 * kATileBytes, 2 * kATileBytes, &full[slot]);
+            umma::bulk_g2s(dst + 2 * kATileBytes, sp.at[l] + (size_t)ti * kSpillTileBytes + st * 2 * kATileBytes, 2 * kATileBytes, &full[slot]);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---- MMA issuer
+        for (int i = 0; i < nstage; i++) {
+            const int slot = i % kDwStages, use = i / kDwStages;
+            umma::mbar_wait(&full[slot], use & 1);
+            umma::fence_after_sync();
+            const int l = (i >> 1) % kNL;
+            const uint32_t idesc = umma::make_idesc_mn(64, g.Kp[l], umma::kFmtBF16);
+            const uint32_t zh = umma::smem_u32(ring + slot * kDwStageBytes), zl = zh + kATileBytes, ah = zl + kATileBytes, al = ah + kATileBytes;
+            const uint32_t d = tmem_base + l * 64;
+            for (int kk = 0; kk < kTile / 16; kk++) {
+                const uint32_t ko = kk * 2 * kSBO_A;                 // 16 samples = two 8-sample groups
+                const uint64_t dzh = umma::make_desc(zh + ko, kSBO_A, kLBO), dzl = umma::make_desc(zl + ko, kSBO_A, kLBO);
+                const uint64_t dah = umma::make_desc(ah + ko, kSBO_A, kLBO), dal = umma::make_desc(al + ko, kSBO_A, kLBO);
+                umma::mma_bf16(d, dzh, dah, idesc, (i >= kNL * 2 || (i & 1) || kk > 0) ? 1u : 0u);   // first stage of a layer clears
+                umma::mma_bf16(d, dzh, dal, idesc, 1u);
+                umma::mma_bf16(d, dzl, dah, idesc, 1u);
+            }
+            umma::commit(&empty[slot]);
+        }
+        umma::commit(done);
+    }
+    __syncwarp();
+    umma::mbar_wait(done, 0);
+    umma::fence_after_sync();
+    // ---- epilogue: lanes 0..15 of warp w hold accumulator rows 16 w .. 16 w + 15
+    float* gW[kNL] = {gW0, gW1, gW2, gW3};
+    if (nstage > 0) {
+        for (int l = 0; l < kNL; l++) {
+            const int m = warp * 16 + lane;
+            for (int c = 0; c < g.Kp[l] / 16; c++) {
+                float v[16];
+                umma::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + l * 64 + c * 16, v);
+                umma::tmem_ld_wait();
+                if (lane < 16 && m < g.N[l]) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const int k = c * 16 + i;
+                        if (k < g.K[l]) atomicAdd(gW[l] + (size_t)m * g.K[l] + k, v[i]);
+                    }
+                }
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_base, 256);
 }
 
 #define ST ((cudaStream_t)stream)
@@ -401,13 +490,16 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
 
 extern "C" {
 
-// Spill buffers (caller allocated, fp32): for l = 0..3  zcat_l [2N, Np_l], acat_l [2N, Kp_l]; Np/Kp = dims padded to 16.
-// grad_lattice and grad_bias_l are accumulated (+=). Weight gradients: dW_l = (zcat_l^T @ acat_l)[:N_l, :K_l].
+// workspace: 8 tile spills (zbar_l, a_{l-1} for l = 0..3), each ceil(N/128) x 64 KB, written and consumed inside this call
+long long psdf_sdf_fused_backward_workspace_bytes(int N) {
+    return (long long)2 * kNL * div_up(N > 0 ? N : 1, kTile) * kSpillTileBytes;
+}
+
+// grad_lattice, grad_W_l [N_l, K_l] and grad_bias_l are accumulated (+=).
 int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
                             const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, const float* g_sdf,
-                            const float* g_grad, const float* g_geom, float* grad_lattice, float* zcat0, float* zcat1, float* zcat2,
-                            float* zcat3, float* acat0, float* acat1, float* acat2, float* acat3, float* gb0, float* gb1, float* gb2,
-                            float* gb3, void* stream) {
+                            const float* g_grad, const float* g_geom, float* grad_lattice, uint8_t* workspace, float* gW0, float* gW1,
+                            float* gW2, float* gW3, float* gb0, float* gb1, float* gb2, float* gb3, void* stream) {
     if (N < 0 || L < 4 || L > kMaxLevels || (L % 4) != 0 || hidden > 64 || hidden % 16 != 0 || out_dim > 64) return PSDF_ERR_UNSUPPORTED;
     if (N == 0) return PSDF_OK;
     FusedParams P;
@@ -418,10 +510,13 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
     if (P.in_dim > 64) return PSDF_ERR_UNSUPPORTED;
     P.g = make_geom(P.in_dim, hidden, out_dim);
     Spill sp;
-    float* z[kNL] = {zcat0, zcat1, zcat2, zcat3};
-    float* a[kNL] = {acat0, acat1, acat2, acat3};
     float* b[kNL] = {gb0, gb1, gb2, gb3};
-    for (int l = 0; l < kNL; l++) { sp.zcat[l] = z[l]; sp.acat[l] = a[l]; sp.gbias[l] = b[l]; }
+    const int ntiles = div_up(N, kTile);
+    for (int l = 0; l < kNL; l++) {
+        sp.zt[l] = workspace + (size_t)(2 * l) * ntiles * kSpillTileBytes;
+        sp.at[l] = workspace + (size_t)(2 * l + 1) * ntiles * kSpillTileBytes;
+        sp.gbias[l] = b[l];
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -430,9 +525,13 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
     if ((size_t)128 * (2 * P.g.Kp[0] + 1) * 4 > (size_t)8 * kATileBytes) return PSDF_ERR_UNSUPPORTED;
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(k_sdf_fused_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_done = true; }
-    const int ntiles = div_up(N, kTile);
     k_sdf_fused_backward<<<min(ntiles, sms), kBwdThreads, smem, ST>>>(P, pos, reinterpret_cast<const float2*>(lattice), scale_factor, shift,
                                                                       window, blob, g_sdf, g_grad, g_geom, grad_lattice, sp);
+    PSDF_CHECK_LAUNCH();
+    const size_t smem_dw = (size_t)kDwStages * kDwStageBytes + 128;
+    static bool attr_dw = false;
+    if (!attr_dw) { cudaFuncSetAttribute(k_sdf_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_dw = true; }
+    k_sdf_dw<<<min(ntiles, sms), 128, smem_dw, ST>>>(P.g, ntiles, sp, gW0, gW1, gW2, gW3);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }

@@ -148,7 +148,19 @@ __device__ __forceinline__ RayIn load_ray(const float* __restrict__ origins, con
 
 // OccupancyGridGPU.cuh:510-703
 // slot_mode 1: ray i owns slots [i*max_per_ray, (i+1)*max_per_ray) (deterministic); 0: global atomic like the reference.
-__global__ void __launch_bounds__(kThreads)
+//
+// One WARP per ray. The reference runs two serial marches per ray (one thread each); here the scalar recurrences are kept
+// bit for bit, but every lane replays them ("uniform serial") so that the memory work hangs off them 32 wide:
+//   pass 1 (length inside occupied voxels): the DDA chain t <- t + dn(t) + eps advances 32 steps per window, lane k latches
+//     step k's voxel and fetches its occupancy, so a window costs ONE load latency; the length is then accumulated in the
+//     original order over the occupied steps;
+//   pass 2 (sample creation): a window speculates that the next w iterations all emit a sample (t advances by `spacing`),
+//     lane j evaluates iteration j (position, voxel, occupancy load, sample stores) and a ballot finds the first iteration
+//     that does not emit; that iteration (skip to the next voxel, with its jitter draw) is then executed serially.
+// The march stops once all n_create samples exist: the reference keeps stepping to t_exit, which changes no output.
+constexpr int kOccWarpsPerBlock = 4;
+template <bool kInvMul>
+__global__ void __launch_bounds__(kOccWarpsPerBlock * 32)
 k_occ_samples_in_occupied(int nr_rays, GridGeom g, const float* __restrict__ origins, const float* __restrict__ dirs,
                           const float* __restrict__ t_entry, const float* __restrict__ t_exit_,
                           const uint8_t* __restrict__ occ, float min_dist, int max_per_ray, int max_nr_samples, Pcg32 rng,
@@ -156,65 +168,79 @@ k_occ_samples_in_occupied(int nr_rays, GridGeom g, const float* __restrict__ ori
                           float* __restrict__ s_z, float* __restrict__ s_dt, float* __restrict__ ray_fixed_dt,
                           int* __restrict__ start_end, int* __restrict__ cur_nr_samples) {
     rng.resolve();
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned kFull = 0xffffffffu;
+    const int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (idx >= nr_rays) return;
     const int nv = g.V * g.V * g.V;
     const float eps = 1e-6f;
     RayIn r = load_ray(origins, dirs, idx);
-    float t_start = t_entry[idx], t_exit = t_exit_[idx];
+    const float t_start = t_entry[idx], t_exit = t_exit_[idx];
+    const float hsx = half_sign(r.dx), hsy = half_sign(r.dy), hsz = half_sign(r.dz);
+    const float Vf = (float)g.V, inv_V = 1.0f / Vf;       // V is a power of two: t / V == t * (1 / V) exactly
 
-    // ---- pass 1: length of the ray inside occupied voxels. The t recurrence runs kBatch steps ahead of the
-    // occupancy loads so each batch costs one L2 latency instead of kBatch.
+    // ---- pass 1. A window runs 32 DDA steps with no control dependence on the voxel index (steps past the end of the
+    // march are computed and discarded), lane k latches step k; the occupancy bytes of window i are consumed after the chain
+    // of window i+1, so their latency hides behind it.
     float t = t_start;
     int steps = 0;
     float occ_len = 0.0f;
     bool alive = (t < t_exit);
+    unsigned p_o = 0;                 // previous window: occupancy byte of this lane's step (0 if the step was not recorded)
+    float p_dn = 0.f, p_t = 0.f;
+    auto consume = [&](unsigned o, float dn, float tt) {
+        unsigned hits = __ballot_sync(kFull, o != 0);
+        while (hits) {                                   // occupied steps, in march order
+            const int k = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const float dnk = __shfl_sync(kFull, dn, k), tk = __shfl_sync(kFull, tt, k);
+            occ_len = __fadd_rn(occ_len, dnk);
+            const float tm = __fsub_rn(tk, eps);
+            if (tm > t_exit) occ_len = __fsub_rn(occ_len, __fsub_rn(tm, t_exit));
+        }
+    };
     while (alive) {
-        int vb[kBatch];
-        float dnb[kBatch], tb[kBatch];
-        int m = 0;
-#pragma unroll
-        for (int k = 0; k < kBatch; k++) {
-            if (alive) {
-                float px = __fmaf_rn(r.dx, t, r.ox), py = __fmaf_rn(r.dy, t, r.oy), pz = __fmaf_rn(r.dz, t, r.oz);
-                int v = pos_to_voxel(px, py, pz, g);
-                if (v >= nv || v < 0) { alive = false; }
-                else {
-                    float dn = dda_step(px, py, pz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, g.V);
-                    t = __fadd_rn(__fadd_rn(t, dn), eps);
-                    vb[k] = v; dnb[k] = dn; tb[k] = t;
-                    m = k + 1;
-                    steps++;
-                    alive = (t < t_exit) && (steps < kMaxSteps);
-                }
-            }
+        int myv = 0;
+        float mydn = 0.f, myt = 0.f;
+        bool myoob = false;
+        float tw = t;
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) {
+            const float px = __fmaf_rn(r.dx, tw, r.ox), py = __fmaf_rn(r.dy, tw, r.oy), pz = __fmaf_rn(r.dz, tw, r.oz);
+            const int v = pos_to_voxel_t<kInvMul>(px, py, pz, g, Vf);
+            const float dn = dda_step_s(px, py, pz, hsx, hsy, hsz, r.ix, r.iy, r.iz, Vf, inv_V);
+            tw = __fadd_rn(__fadd_rn(tw, dn), eps);
+            if (lane == k) { myv = v; mydn = dn; myt = tw; myoob = (v >= nv || v < 0); }
         }
-        uint8_t ob[kBatch];
-#pragma unroll
-        for (int k = 0; k < kBatch; k++) ob[k] = (k < m) ? __ldg(occ + vb[k]) : 0;
-#pragma unroll
-        for (int k = 0; k < kBatch; k++) {
-            if (k < m && ob[k]) {
-                occ_len = __fadd_rn(occ_len, dnb[k]);
-                float tm = __fsub_rn(tb[k], eps);
-                if (tm > t_exit) occ_len = __fsub_rn(occ_len, __fsub_rn(tm, t_exit));
-            }
-        }
+        // step k+1 is attempted iff step k was inside the grid and left the march alive
+        const bool last = myoob || !(myt < t_exit) || !(steps + lane + 1 < kMaxSteps);
+        const unsigned stop = __ballot_sync(kFull, last);
+        const int first = stop ? __ffs(stop) - 1 : 32;
+        int m = 32;
+        if (first < 32) { m = __shfl_sync(kFull, (int)myoob, first) ? first : first + 1; alive = false; }
+        if (m > 0) t = __shfl_sync(kFull, myt, m - 1);
+        steps += m;
+        const unsigned o = (lane < m) ? (unsigned)__ldg(occ + myv) : 0u;     // consumed one window later
+        consume(p_o, p_dn, p_t);
+        p_o = o; p_dn = mydn; p_t = myt;
     }
+    consume(p_o, p_dn, p_t);
 
     int n_create = (int)__fdiv_rn(occ_len, min_dist);
     n_create = min(max(n_create, 0), max_per_ray);
-    float spacing = __fdiv_rn(occ_len, (float)n_create);
+    const float spacing = __fdiv_rn(occ_len, (float)n_create);
 
     if (n_create > 1) {
-        int start;
-        if (slot_mode == 1) { start = idx * max_per_ray; atomicAdd(cur_nr_samples, n_create); }
-        else start = atomicAdd(cur_nr_samples, n_create);
-        start_end[2 * idx] = start;
-        start_end[2 * idx + 1] = start + n_create;
-        ray_fixed_dt[idx] = spacing;
-        if (start + n_create > max_nr_samples) return;
-
+        int start = 0;
+        if (lane == 0) {
+            if (slot_mode == 1) { start = idx * max_per_ray; atomicAdd(cur_nr_samples, n_create); }
+            else start = atomicAdd(cur_nr_samples, n_create);
+        }
+        start = __shfl_sync(kFull, start, 0);
+        if (start + n_create > max_nr_samples) {
+            if (lane == 0) { start_end[2 * idx] = start; start_end[2 * idx + 1] = start + n_create; ray_fixed_dt[idx] = spacing; }
+            return;
+        }
         t = t_start;
         steps = 0;
         if (jitter) {
@@ -223,42 +249,88 @@ k_occ_samples_in_occupied(int nr_rays, GridGeom g, const float* __restrict__ ori
         }
         int created = 0;
         float last_z = 0.0f;
-        while (t < t_exit && steps < kMaxSteps) {
-            t = clampf(t, t_start, t_exit);
-            float px = __fmaf_rn(r.dx, t, r.ox), py = __fmaf_rn(r.dy, t, r.oy), pz = __fmaf_rn(r.dz, t, r.oz);
-            int v = pos_to_voxel(px, py, pz, g);
-            if (v >= nv || v < 0) break;
-            if (__ldg(occ + v) && created < n_create) {
-                int s = start + created;
+        while (t < t_exit && steps < kMaxSteps && created < n_create) {
+            // ---- emit window: the next w iterations are assumed to create a sample each (t advances by the spacing)
+            const int w = min(32, n_create - created);
+            float tj = t, mine = t;
+            for (int j = 1; j < w; j++) { tj = __fadd_rn(tj, spacing); if (lane == j) mine = tj; }
+            const bool in = (lane < w) && (mine < t_exit) && (steps + lane < kMaxSteps);
+            const float tc = clampf(mine, t_start, t_exit);
+            const float px = __fmaf_rn(r.dx, tc, r.ox), py = __fmaf_rn(r.dy, tc, r.oy), pz = __fmaf_rn(r.dz, tc, r.oz);
+            const int v = pos_to_voxel_t<kInvMul>(px, py, pz, g, Vf);
+            const bool inside = in && !(v >= nv || v < 0);
+            const bool emit = inside && __ldg(occ + v);
+            const unsigned nem = ~__ballot_sync(kFull, emit);
+            const int e = min(nem ? __ffs(nem) - 1 : 32, w);                 // leading iterations that emit
+            if (lane < e) {
+                const int s = start + created + lane;
                 s_pos[3 * s] = px; s_pos[3 * s + 1] = py; s_pos[3 * s + 2] = pz;
                 s_dirs[3 * s] = r.dx; s_dirs[3 * s + 1] = r.dy; s_dirs[3 * s + 2] = r.dz;
-                s_z[s] = t;
+                s_z[s] = tc;
                 s_dt[s] = spacing;
-                last_z = t;
-                t = __fadd_rn(t, spacing);
-                created++;
-            } else {
-                float delta = dda_step(px, py, pz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, g.V);
-                if (jitter) delta = __fmaf_rn(rng.next_float(), spacing, delta);
-                t = __fadd_rn(__fadd_rn(t, delta), eps);
             }
-            steps++;
+            if (e > 0) {
+                last_z = __shfl_sync(kFull, tc, e - 1);
+                for (int j = 0; j < e; j++) t = __fadd_rn(clampf(t, t_start, t_exit), spacing);
+                created += e;
+                steps += e;
+            }
+            if (e == w) continue;
+            // iteration e does not emit: it ends the march (t_exit / step limit / outside the grid) or starts a run of skips
+            if (!__shfl_sync(kFull, (int)inside, e)) break;
+            // ---- skip windows: the next 32 iterations are assumed to skip to the next voxel (DDA step + jitter draw); lane k
+            // latches the state at the START of iteration k and tests that position; the first iteration that would not skip
+            // (occupied voxel, end of the march) is where the state is rolled back to
+            bool finished = false;
+            while (true) {
+                float myt = 0.f;
+                uint64_t myrng = 0;
+                int myv2 = 0;
+                bool myoob2 = false;
+                float tw = t;
+#pragma unroll 4
+                for (int k = 0; k < 32; k++) {
+                    const float tk = clampf(tw, t_start, t_exit);
+                    const float qx = __fmaf_rn(r.dx, tk, r.ox), qy = __fmaf_rn(r.dy, tk, r.oy), qz = __fmaf_rn(r.dz, tk, r.oz);
+                    const int v2 = pos_to_voxel_t<kInvMul>(qx, qy, qz, g, Vf);
+                    if (lane == k) { myt = tw; myrng = rng.state; myv2 = v2; myoob2 = (v2 >= nv || v2 < 0); }
+                    float delta = dda_step_s(qx, qy, qz, hsx, hsy, hsz, r.ix, r.iy, r.iz, Vf, inv_V);
+                    if (jitter) delta = __fmaf_rn(rng.next_float(), spacing, delta);
+                    tw = __fadd_rn(__fadd_rn(tk, delta), eps);
+                }
+                const bool in2 = (myt < t_exit) && (steps + lane < kMaxSteps);
+                const bool occ2 = in2 && !myoob2 && __ldg(occ + myv2);
+                const unsigned stop2 = __ballot_sync(kFull, !in2 || myoob2 || occ2);
+                const int f = stop2 ? __ffs(stop2) - 1 : 32;
+                if (f == 32) {                       // 32 confirmed skips; the generator already sits after the 32nd draw
+                    t = tw;
+                    steps += 32;
+                    if (!(t < t_exit && steps < kMaxSteps)) { finished = true; break; }
+                    continue;
+                }
+                t = __shfl_sync(kFull, myt, f);
+                const uint32_t lo = __shfl_sync(kFull, (uint32_t)myrng, f), hi = __shfl_sync(kFull, (uint32_t)(myrng >> 32), f);
+                rng.state = ((uint64_t)hi << 32) | lo;
+                steps += f;
+                finished = !__shfl_sync(kFull, (int)occ2, f);      // stopped by the end of the march, not by an occupied voxel
+                break;
+            }
+            if (finished) break;
         }
-        if (created > 0) s_dt[start + created - 1] = clampf(__fsub_rn(t_exit, last_z), 0.0f, spacing);
-        for (int i = created; i < n_create; i++) {
-            int s = start + i;
+        for (int i = created + lane; i < n_create; i += 32) {
+            const int s = start + i;
             s_pos[3 * s] = 0; s_pos[3 * s + 1] = 0; s_pos[3 * s + 2] = 0;
             s_dirs[3 * s] = 0; s_dirs[3 * s + 1] = 0; s_dirs[3 * s + 2] = 0;
             s_z[s] = -1.0f;
             s_dt[s] = 0;
         }
-        start_end[2 * idx + 1] = start + created;
-        if (created <= 2) {
-            ray_fixed_dt[idx] = 0;
-            start_end[2 * idx] = 0;
-            start_end[2 * idx + 1] = 0;
+        __syncwarp();
+        if (lane == 0) {
+            if (created > 0) s_dt[start + created - 1] = clampf(__fsub_rn(t_exit, last_z), 0.0f, spacing);
+            if (created <= 2) { ray_fixed_dt[idx] = 0; start_end[2 * idx] = 0; start_end[2 * idx + 1] = 0; }
+            else { ray_fixed_dt[idx] = spacing; start_end[2 * idx] = start; start_end[2 * idx + 1] = start + created; }
         }
-    } else {
+    } else if (lane == 0) {
         ray_fixed_dt[idx] = 0;
         start_end[2 * idx] = 0;
         start_end[2 * idx + 1] = 0;
@@ -741,8 +813,9 @@ int psdf_occ_compute_samples_in_occupied_regions(int nr_rays, int V, float exten
                                                  int* ray_start_end, int* cur_nr_samples, void* stream) {
     if (nr_rays <= 0) return nr_rays == 0 ? PSDF_OK : PSDF_ERR_ARG;
     if (slot_mode == 1 && (long long)nr_rays * max_per_ray > (long long)max_nr_samples) return PSDF_ERR_ARG;
-    // 128-thread blocks: 512 rays spread over 4 SMs instead of 2; the kernel is latency bound, not occupancy bound
-    k_occ_samples_in_occupied<<<div_up(nr_rays, 64), 64, 0, ST>>>(nr_rays, geom(V, extent, trans), origins, dirs, t_entry, t_exit,
+    const GridGeom gg = geom(V, extent, trans);
+    auto kern = gg.inv_extent != 0.0f ? k_occ_samples_in_occupied<true> : k_occ_samples_in_occupied<false>;
+    kern<<<div_up(nr_rays, kOccWarpsPerBlock), kOccWarpsPerBlock * 32, 0, ST>>>(nr_rays, gg, origins, dirs, t_entry, t_exit,
                                                                  occ, min_dist, max_per_ray, max_nr_samples,
                                                                  Pcg32(rng_state, rng_inc), jitter != 0, slot_mode, s_pos,
                                                                  s_dirs, s_z, s_dt, ray_fixed_dt, ray_start_end,

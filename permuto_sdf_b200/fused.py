@@ -11,6 +11,38 @@ from ._lib import call, load_library
 from .permuto_sdf import RaySamplesPacked
 
 
+def splitk_tn(a, b, slabs=64):
+    """a^T b for tall operands a [R, M], b [R, K] (weight gradients: the reduction runs over the sample axis). A plain library
+    GEMM gives this to one or two CTAs looping over all R rows (latency bound, ~180 us at R = 128 k); as a batched GEMM over
+    `slabs` row slabs followed by a small sum it fills the GPU."""
+    R = a.shape[0]
+    if R < 32 * slabs:
+        return a.t() @ b
+    main = R // slabs * slabs
+    out = torch.bmm(a[:main].view(slabs, -1, a.shape[1]).transpose(1, 2), b[:main].view(slabs, -1, b.shape[1])).sum(0)
+    if main != R:
+        out = out + a[main:].t() @ b[main:]
+    return out
+
+
+class SplitKLinearFn(torch.autograd.Function):
+    """F.linear(x, w, bias) whose weight gradient uses splitk_tn (the MLP layers around the fused kernels)"""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        ctx.save_for_backward(x, w)
+        return torch.addmm(bias, x, w.t())
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        gx = g @ w if ctx.needs_input_grad[0] else None
+        gw = splitk_tn(g, x) if ctx.needs_input_grad[1] else None
+        gb = g.sum(0) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb
+
+
 class FusedSDF:
     def __init__(self, model_sdf):
         self.model = model_sdf
@@ -106,22 +138,19 @@ class _FusedSDFTrainFn(torch.autograd.Function):
         dev = points.device
         dims_k = [fused.in_dim, fused.hidden, fused.hidden, fused.hidden]
         dims_n = [fused.hidden, fused.hidden, fused.hidden, fused.out_dim]
-        zcat = [torch.empty(2 * N, _pad16(n), device=dev) for n in dims_n]
-        acat = [torch.empty(2 * N, _pad16(k), device=dev) for k in dims_k]
+        gW = [torch.zeros(n, k, device=dev) for n, k in zip(dims_n, dims_k)]
         gb = [torch.zeros(n, device=dev) for n in dims_n]
-        g_lat = torch.zeros_like(lattice)
+        ws = torch.empty(int(load_library().psdf_sdf_fused_backward_workspace_bytes(N)), dtype=torch.uint8, device=dev)
+        # with a flat-buffer optimizer the hash-table gradient is scattered straight into lattice.grad (no 33 MB zero-fill
+        # plus accumulate pass per call); autograd then gets no gradient for the table from this node
+        in_place = getattr(enc, "grad_in_place", False) and lattice.grad is not None and lattice.grad.is_contiguous()
+        g_lat = lattice.grad if in_place else torch.zeros_like(lattice)
         c = lambda t: None if t is None else t.contiguous()
+        # kernel 1: reverse sweep + lattice scatter + operand-tile spill; kernel 2: dW = zbar^T a on the tensor cores
         call("psdf_sdf_fused_backward", N, enc.nr_levels, enc.capacity, points, lattice.detach(), enc.scale_factor, enc.shift_tensor(), window,
-             enc.concat_points_scaling, fused.hidden, fused.out_dim, fused.blob, c(g_sdf), c(g_grad), c(g_geom), g_lat, zcat[0], zcat[1], zcat[2],
-             zcat[3], acat[0], acat[1], acat[2], acat[3], gb[0], gb[1], gb[2], gb[3])
-        # dW_l = zcat_l^T acat_l: a [Np, 2N] x [2N, Kp] library GEMM whose reduction dimension is the sample axis; split-K as a
-        # batched GEMM (one slab of samples per batch entry) so that it fills the GPU instead of 1-2 CTAs looping over 2N rows
-        S = 64 if (2 * N) % 64 == 0 and N >= 2048 else 1
-        gW = []
-        for l in range(4):
-            z3, a3 = zcat[l].view(S, -1, zcat[l].shape[1]), acat[l].view(S, -1, acat[l].shape[1])
-            gW.append(torch.bmm(z3.transpose(1, 2), a3).sum(0)[:dims_n[l], :dims_k[l]])
-        return (None, g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
+             enc.concat_points_scaling, fused.hidden, fused.out_dim, fused.blob, c(g_sdf), c(g_grad), c(g_geom), g_lat, ws, gW[0], gW[1], gW[2],
+             gW[3], gb[0], gb[1], gb[2], gb[3])
+        return (None, None if in_place else g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
 
 
 # ================================================================================================ NeuS compositing + losses
@@ -195,3 +224,53 @@ def neus_render_loss(rsp, sdf, sdf_gradients, rgb_samples, inv_s, cos_anneal_rat
         raise ValueError("neus_render_loss: sdf must have one row per packed sample")
     return _NeusRenderLossFn.apply(rsp, sdf.reshape(-1), sdf_gradients, rgb_samples, inv_s, bg_rgb, cos_anneal_ratio,
                                    gt_rgb.detach().contiguous(), f(gt_mask), hit_u8, float(eikonal_weight), float(mask_weight))
+
+
+# ================================================================================================ colour-network helpers
+class LipschitzNormFn(torch.autograd.Function):
+    """LipshitzMLP.normalization (models.py:96-110) in one kernel each way (csrc/rgb_misc.cu): w * min(1, softplus(c) / sum|w|)"""
+
+    @staticmethod
+    def forward(ctx, w, c):
+        wc, cc = w.detach().contiguous(), c.detach().reshape(1).contiguous()
+        out = torch.empty_like(wc)
+        call("psdf_lipschitz_normalize", wc.shape[0], wc.shape[1], wc, cc, out)
+        ctx.save_for_backward(wc, cc)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        wc, cc = ctx.saved_tensors
+        gw = torch.empty_like(wc)
+        gc = torch.zeros(1, device=wc.device) if ctx.needs_input_grad[1] else None
+        call("psdf_lipschitz_normalize_backward", wc.shape[0], wc.shape[1], wc, cc, g.contiguous(), gw, gc)
+        return gw, gc
+
+
+class CalibSigmoidFn(torch.autograd.Function):
+    """Colorcal.calib_RGB_samples_packed followed by the sigmoid of the colour head (models.py:395-414, 677-741) on packed samples,
+    one kernel each way; img_indices is per ray; rows outside every ray stay zero"""
+
+    @staticmethod
+    def forward(ctx, x, ray_start_end_idx, img_indices, weight_delta, bias, fixed_img):
+        xc = x.detach().contiguous()
+        out = torch.zeros_like(xc)
+        R, N = ray_start_end_idx.shape[0], xc.shape[0]
+        img = None if img_indices is None else img_indices.detach().reshape(-1).to(torch.int32).contiguous()
+        wd = None if weight_delta is None else weight_delta.detach().contiguous()
+        bs = None if bias is None else bias.detach().contiguous()
+        rsp = (R, N, ray_start_end_idx, 0, 0)
+        call("psdf_calib_sigmoid_forward", *rsp, xc, img if wd is not None else None, wd, bs, int(fixed_img), out)
+        ctx.rsp, ctx.fixed = rsp, int(fixed_img)
+        ctx.save_for_backward(xc, out, img, wd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xc, out, img, wd = ctx.saved_tensors
+        gx = torch.zeros_like(xc)
+        need_p = wd is not None and (ctx.needs_input_grad[3] or ctx.needs_input_grad[4])
+        gwd = torch.zeros_like(wd) if need_p else None
+        gbs = torch.zeros_like(wd) if need_p else None
+        call("psdf_calib_sigmoid_backward", *ctx.rsp, xc, out, g.contiguous(), img if wd is not None else None, wd, ctx.fixed, gx, gwd, gbs)
+        return gx, None, None, gwd, gbs, None

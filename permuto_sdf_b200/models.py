@@ -18,6 +18,21 @@ from .permuto_sdf import PermutoSDF, RaySamplesPacked
 from .volume_rendering import VolumeRenderingNerf, VolumeRenderingNeus
 
 
+class _LazySplitK:
+    """fused.py imports models lazily; resolve SplitKLinearFn on first use"""
+    fn = None
+
+    @staticmethod
+    def apply(x, w, b):
+        if _LazySplitK.fn is None:
+            from .fused import SplitKLinearFn as f
+            _LazySplitK.fn = f
+        return _LazySplitK.fn.apply(x, w, b)
+
+
+SplitKLinearFn = _LazySplitK
+
+
 class DeviceIter:
     """Iteration number held twice: `host` (int) drives Python control flow, `dev` (0-d float32 CUDA tensor with the same
     value) feeds every quantity that changes from one iteration to the next (map_range_val ramps). A training iteration
@@ -119,6 +134,8 @@ class LipshitzMLP(torch.nn.Module):
             max_w = torch.max(torch.sum(torch.abs(l.weight), dim=1))
             self.lipshitz_bound_per_layer.append(torch.nn.Parameter(torch.ones(1, device=l.weight.device) * max_w.detach() * 2))
 
+    fused_normalization = True      # CUDA weights: one kernel each way (csrc/rgb_misc.cu) instead of ~6 + ~10 element-wise launches
+
     @staticmethod
     def normalization(w, softplus_ci):
         absrowsum = torch.sum(torch.abs(w), dim=1)
@@ -134,8 +151,12 @@ class LipshitzMLP(torch.nn.Module):
     def forward(self, x):
         n = len(self.layers)
         for i, l in enumerate(self.layers):
-            w = self.normalization(l.weight, F.softplus(self.lipshitz_bound_per_layer[i]))
-            x = F.linear(x, w, l.bias)
+            if self.fused_normalization and l.weight.is_cuda:
+                from .fused import LipschitzNormFn
+                w = LipschitzNormFn.apply(l.weight, self.lipshitz_bound_per_layer[i])
+            else:
+                w = self.normalization(l.weight, F.softplus(self.lipshitz_bound_per_layer[i]))
+            x = SplitKLinearFn.apply(x, w, l.bias) if (x.is_cuda and x.dim() == 2) else F.linear(x, w, l.bias)
             if not (i == n - 1 and self.last_layer_linear):
                 x = F.gelu(x)
         return x
@@ -244,6 +265,7 @@ class RGB(torch.nn.Module):
         self.c2f = permuto_enc.Coarse2Fine(nr_levels)
         self.nr_iters_for_c2f = nr_iters_for_c2f
         self.last_iter_nr = sys.maxsize
+        self.fused_head = True
 
     def forward(self, points, samples_dirs, sdf_gradients, geom_feat, iter_nr, model_colorcal=None, img_indices=None,
                 ray_start_end_idx=None):
@@ -256,6 +278,13 @@ class RGB(torch.nn.Module):
         normals = F.normalize(sdf_gradients.view(-1, 3), dim=1)
         x = torch.cat([feat, dirs_enc, normals, geom_feat], 1)
         x = self.mlp(x)
+        if self.fused_head and x.is_cuda and ray_start_end_idx is not None:
+            # colour calibration + sigmoid in one kernel each way (csrc/rgb_misc.cu)
+            from .fused import CalibSigmoidFn
+            if model_colorcal is not None:
+                return CalibSigmoidFn.apply(x, ray_start_end_idx, img_indices, model_colorcal.weight_delta, model_colorcal.bias,
+                                            model_colorcal.idx_with_fixed_calib)
+            return CalibSigmoidFn.apply(x, ray_start_end_idx, None, None, None, -1)
         if model_colorcal is not None:
             x = model_colorcal.calib_RGB_samples_packed(x, img_indices, ray_start_end_idx)
         return torch.sigmoid(x)

@@ -36,6 +36,8 @@ class _EncodeFn(torch.autograd.Function):
         lattice, positions, window = ctx.saved_tensors
         need_l, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         g_l, g_p = _EncodeBackFn.apply(lattice, positions, window, grad_out.contiguous(), ctx.mod, need_l, need_p)
+        if need_l and g_l.numel() == 1 and lattice.numel() != 1:
+            g_l = None          # already accumulated into lattice.grad (grad_in_place)
         return (g_l if need_l else None), (g_p if need_p else None), None, None
 
 
@@ -44,13 +46,15 @@ class _EncodeBackFn(torch.autograd.Function):
     def forward(ctx, lattice, positions, window, grad_out, mod, need_l, need_p):
         D, L, F, T = _enc_consts(mod)
         N = positions.shape[0]
-        g_l = torch.zeros_like(lattice) if need_l else None
+        # grad_in_place (flat-buffer optimizer): scatter straight into lattice.grad instead of a fresh zero-filled table
+        in_place = need_l and getattr(mod, "grad_in_place", False) and lattice.grad is not None and lattice.grad.is_contiguous()
+        g_l = (lattice.grad if in_place else torch.zeros_like(lattice)) if need_l else None
         g_p = torch.empty_like(positions) if need_p else None
         call("psdf_enc_backward", N, D, L, F, T, positions, lattice, mod.scale_factor, mod.shift_tensor(), window,
              1 if mod.concat_points else 0, mod.concat_points_scaling, grad_out, g_l, g_p)
         ctx.mod = mod
         ctx.save_for_backward(lattice, positions, window, grad_out)
-        if g_l is None:
+        if g_l is None or in_place:
             g_l = torch.zeros(1, device=positions.device)
             ctx.mark_non_differentiable(g_l)
         if g_p is None:
@@ -104,6 +108,7 @@ class PermutoEncoding(torch.nn.Module):
         self.random_shift_per_level = torch.nn.Parameter(shift.to(dev), requires_grad=False)
         self.register_buffer("scale_factor", self.compute_scale_factor(self.scale_per_level, self.pos_dim).to(dev))
         self._ones = None
+        self.grad_in_place = False      # True: backward scatters into lattice_values.grad directly (set by the flat-buffer optimizer path)
 
     @staticmethod
     def compute_scale_factor(sigmas, pos_dim):

@@ -262,6 +262,9 @@ class Trainer:
         if optimizer == "fused":
             from .optim import FusedAdamW      # our dense AdamW kernel over flat buffers (csrc/optim.cu)
             self.optimizer = FusedAdamW(groups, betas=(0.9, 0.99), eps=1e-15, lr=hp.lr)
+            for m in (self.model_sdf, self.model_rgb, self.model_bg):     # .grad buffers exist for good: scatter into them directly
+                if m is not None:
+                    m.encoding.grad_in_place = True
         else:
             self.optimizer = torch.optim.AdamW(groups, amsgrad=False, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, lr=hp.lr)
         self.iter_nr = 0

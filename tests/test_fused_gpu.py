@@ -148,5 +148,8 @@ def test_umma_transposed_gemm_weight_gradient_layout(cuda, M, N):
         lane = int(err.argmin())
         assert float(err[lane]) < 2e-3 * float(want.abs().max()), "row %d not found in TMEM (best lane %d, err %g)" % (m, lane, float(err[lane]))
         lanes.append(lane)
-    print("M=%d N=%d accumulator row -> lane:" % (M, N), lanes)
+    import os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/umma_m64_layout.txt", "a") as f:
+        f.write("M=%d N=%d accumulator row -> TMEM lane: %s\n" % (M, N, lanes))
     assert lanes == list(range(M)) or lanes == [(m // 16) * 32 + (m % 16) for m in range(M)], lanes

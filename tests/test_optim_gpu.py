@@ -36,3 +36,31 @@ def test_fused_adamw_matches_torch(cuda):
     before = pa[0].detach().clone()
     ours.step(grad_scale=0.5)
     assert not torch.equal(before, pa[0])
+
+
+def test_fused_adamw_device_step_under_cuda_graph(cuda):
+    """step count kept on the device + the step captured in a CUDA graph: replays track an eagerly stepped twin"""
+    from permuto_sdf_b200.optim import FusedAdamW
+    torch.manual_seed(1)
+    pa = [torch.nn.Parameter(torch.randn(4096, device="cuda")), torch.nn.Parameter(torch.randn(33, 7, device="cuda"))]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = FusedAdamW([{"params": pa, "weight_decay": 0.01, "lr": 1e-2}], betas=(0.9, 0.99), eps=1e-15)
+    ob = FusedAdamW([{"params": pb, "weight_decay": 0.01, "lr": 1e-2}], betas=(0.9, 0.99), eps=1e-15)
+    oa.device_step = True
+    oa.step_dev = torch.zeros(1, dtype=torch.int32, device="cuda")
+    grads = [torch.randn_like(oa.flat_grad) for _ in range(5)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):                      # warm-up outside the capture
+        oa.flat_grad.copy_(grads[0]); oa.step()
+    torch.cuda.current_stream().wait_stream(side)
+    ob.flat_grad.copy_(grads[0]); ob.step()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        oa.step()
+    oa.step_count -= 1
+    for k in range(1, 5):
+        oa.flat_grad.copy_(grads[k]); g.replay(); oa.step_count += 1
+        ob.flat_grad.copy_(grads[k]); ob.step()
+        assert int(oa.step_dev) == ob.step_count == k + 1
+        assert torch.allclose(oa.flat_param, ob.flat_param, rtol=1e-5, atol=1e-6), "diverged at replay %d" % k

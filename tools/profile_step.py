@@ -22,6 +22,9 @@ def main():
     tr = Trainer(hp, nr_levels=16, capacity=2 ** 18, sdf_hidden=64, nr_images=8, occupancy_resolution=256, seed=0, optimizer="fused")
     tr.set_analytic_scene()
     tr.iter_nr = 20000
+    if os.environ.get("STATIC", "1") == "1":     # shapes of the CUDA-graph mode (kernel times as inside the replayed graph)
+        from permuto_sdf import RaySamplesPacked
+        RaySamplesPacked.static_capacity = True
     reel = bench.analytic_reel(8, 600, 800, 1000.0, dev)
     gen = torch.Generator().manual_seed(1)
 
