@@ -224,6 +224,28 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
                             const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, const float* g_sdf,
                             const float* g_grad, const float* g_geom, float* grad_lattice, uint8_t* workspace, float* gW0, float* gW1,
                             float* gW2, float* gW3, float* gb0, float* gb1, float* gb2, float* gb3, void* stream);
+/* ---------------------------------------------------------------- fused colour network (RGB.forward, permuto_sdf_py/models/models.py:309-420)
+ * encoding(points) | SH_5(dirs) | normalize(sdf_grad) | geom [N,32] -> 4-layer GELU MLP (in -> h1 -> h2 -> h3 -> 3) on the tensor
+ * cores; out [N,3] is the linear output (colour calibration + sigmoid: psdf_calib_sigmoid_*). Weights are passed as a packed
+ * operand blob (psdf_rgb_mlp_pack of the already Lipschitz-normalised matrices W_l [N_l,K_l] + biases); L % 4 == 0,
+ * in_dim = 2L + 64 <= 128, h* <= 128 and % 16 == 0. */
+long long psdf_rgb_mlp_blob_bytes(int in_dim, int h1, int h2, int h3, int out_dim);
+int psdf_rgb_mlp_pack(int in_dim, int h1, int h2, int h3, int out_dim, const float* W0, const float* b0, const float* W1, const float* b1,
+                      const float* W2, const float* b2, const float* W3, const float* b3, uint8_t* blob, void* stream);
+int psdf_rgb_fused_forward(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
+                           const float* lattice, const float* scale_factor, const float* shift, const float* window, float points_scaling,
+                           int h1, int h2, int h3, const uint8_t* blob, float* out, void* stream);
+
+/* backward of psdf_rgb_fused_forward: g_out [N,3] = d loss / d out -> grad_lattice (+=), g_sdf_grad [N,3] (=), g_geom [N,32] (=),
+ * weight gradients gW_l [N_l,K_l] (+=, wrt the normalised matrices) and bias gradients gb_l (+=). workspace:
+ * psdf_rgb_fused_backward_workspace_bytes(N) bytes of scratch. */
+long long psdf_rgb_fused_backward_workspace_bytes(int N);
+int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
+                            const float* lattice, const float* scale_factor, const float* shift, const float* window, float points_scaling,
+                            int h1, int h2, int h3, const uint8_t* blob, const float* g_out, float* grad_lattice, float* g_sdf_grad,
+                            float* g_geom, uint8_t* workspace, float* gW0, float* gW1, float* gW2, float* gW3, float* gb0, float* gb1,
+                            float* gb2, float* gb3, void* stream);
+
 /* ---------------------------------------------------------------- dense fused AdamW (torch.optim.AdamW / apex FusedAdam math,
  * train_permuto_sdf.py:293-304); step >= 1 is the incremented step count; grad is multiplied by grad_scale and, when
  * zero_grad != 0, reset to zero in the same pass. Pointers 16-byte aligned. step_dev [1] (device int32), when not NULL,

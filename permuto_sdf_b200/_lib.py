@@ -153,7 +153,7 @@ def call(name, *args):
 
 # ---- instrumentation used by bench.py: count C-ABI calls / kernel launches and time them with CUDA events on the
 # launching stream. Kernel launches per entry point (the rest launch exactly one kernel):
-_KERNELS_PER_CALL = {"psdf_packed_compact_scan": 2, "psdf_vr_combine_uniform_samples_with_imp": 3, "psdf_sdf_fused_backward": 2}
+_KERNELS_PER_CALL = {"psdf_packed_compact_scan": 2, "psdf_vr_combine_uniform_samples_with_imp": 3, "psdf_sdf_fused_backward": 2, "psdf_rgb_fused_backward": 2}
 _STATS = None
 
 

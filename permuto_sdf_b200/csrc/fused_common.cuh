@@ -23,9 +23,8 @@ struct MlpGeom {
     int total_t;
 };
 __host__ __device__ inline int pad16(int v) { return (v + 15) & ~15; }
-inline MlpGeom make_geom(int in_dim, int hidden, int out_dim) {
+inline MlpGeom make_geom_dims(const int* dims) {
     MlpGeom g;
-    int dims[kNL + 1] = {in_dim, hidden, hidden, hidden, out_dim};
     int off = 0;
     for (int l = 0; l < kNL; l++) {
         g.K[l] = dims[l]; g.N[l] = dims[l + 1];
@@ -44,6 +43,10 @@ inline MlpGeom make_geom(int in_dim, int hidden, int out_dim) {
     }
     g.total_t = (off + 127) & ~127;
     return g;
+}
+inline MlpGeom make_geom(int in_dim, int hidden, int out_dim) {
+    int dims[kNL + 1] = {in_dim, hidden, hidden, hidden, out_dim};
+    return make_geom_dims(dims);
 }
 
 // weights [N][K] fp32 (torch.nn.Linear layout) -> hi/lo bf16 in the UMMA K-major core-matrix layout + fp32 bias;
@@ -202,6 +205,46 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a_hi,
         umma::mma_bf16(tmem_d, dah, dwl, idesc, 1u);
         umma::mma_bf16(tmem_d, dal, dwh, idesc, 1u);
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------- backward helpers
+constexpr unsigned kFull = 0xffffffffu;
+__device__ __forceinline__ float2 add_peers2(unsigned peers, float2 x, int lane) {
+    int rel = __popc(peers << (31 - lane) << 1);
+    peers &= (0xfffffffeu << lane);
+    while (__any_sync(kFull, peers)) {
+        int next = __ffs(peers);
+        float tx = __shfl_sync(kFull, x.x, (next - 1) & 31);
+        float ty = __shfl_sync(kFull, x.y, (next - 1) & 31);
+        if (next) { x.x += tx; x.y += ty; }
+        int done = rel & 1;
+        peers &= __ballot_sync(kFull, !done);
+        rel >>= 1;
+    }
+    return x;
+}
+__device__ __forceinline__ void red_v2(float* addr, float2 v) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+// column sums of 16 per-lane values over the 32 lanes of a warp with 16 shuffles (halving butterfly): afterwards both
+// lanes of the pair {2p, 2p+1} hold the sum of column `col` = bit-reversal-free index built from lane bits 4..1.
+__device__ __forceinline__ float colsum16(const float* v, int lane, int& col) {
+    float a[8], b[4], c[2], d;
+    bool up = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i]; a[i] = keep + __shfl_xor_sync(kFull, send, 16); }
+    up = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { float send = up ? a[i] : a[i + 4], keep = up ? a[i + 4] : a[i]; b[i] = keep + __shfl_xor_sync(kFull, send, 8); }
+    up = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 2; i++) { float send = up ? b[i] : b[i + 2], keep = up ? b[i + 2] : b[i]; c[i] = keep + __shfl_xor_sync(kFull, send, 4); }
+    up = lane & 2;
+    { float send = up ? c[0] : c[1], keep = up ? c[1] : c[0]; d = keep + __shfl_xor_sync(kFull, send, 2); }
+    d += __shfl_xor_sync(kFull, d, 1);
+    col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+    return d;
 }
 
 

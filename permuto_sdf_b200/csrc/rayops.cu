@@ -10,6 +10,7 @@
 // coalesced accesses. Slots in the sample pool are deterministic (ray * stride) rather than handed out
 // by a global atomic, with the reference's atomic order available as slot_mode=0.
 #include "common.cuh"
+#include "sh.cuh"
 #include "../../include/psdf_b200.h"
 
 using namespace psdf;
@@ -200,18 +201,21 @@ k_occ_samples_in_occupied(int nr_rays, GridGeom g, const float* __restrict__ ori
         }
     };
     while (alive) {
-        int myv = 0;
-        float mydn = 0.f, myt = 0.f;
-        bool myoob = false;
+        // the chain carries only what the recurrence needs (position -> DDA step -> t); lane k latches the t at the start of
+        // step k and its step length, and derives its voxel (Morton index) from that t afterwards, 32 lanes in parallel
+        float myt0 = 0.f, mydn = 0.f;
         float tw = t;
 #pragma unroll 8
         for (int k = 0; k < 32; k++) {
             const float px = __fmaf_rn(r.dx, tw, r.ox), py = __fmaf_rn(r.dy, tw, r.oy), pz = __fmaf_rn(r.dz, tw, r.oz);
-            const int v = pos_to_voxel_t<kInvMul>(px, py, pz, g, Vf);
             const float dn = dda_step_s(px, py, pz, hsx, hsy, hsz, r.ix, r.iy, r.iz, Vf, inv_V);
+            if (lane == k) { myt0 = tw; mydn = dn; }
             tw = __fadd_rn(__fadd_rn(tw, dn), eps);
-            if (lane == k) { myv = v; mydn = dn; myt = tw; myoob = (v >= nv || v < 0); }
         }
+        float myt = __shfl_down_sync(kFull, myt0, 1);           // t after this lane's step = t at the start of the next one
+        if (lane == 31) myt = tw;
+        const int myv = pos_to_voxel_t<kInvMul>(__fmaf_rn(r.dx, myt0, r.ox), __fmaf_rn(r.dy, myt0, r.oy), __fmaf_rn(r.dz, myt0, r.oz), g, Vf);
+        const bool myoob = (myv >= nv || myv < 0);
         // step k+1 is attempted iff step k was inside the grid and left the march alive
         const bool last = myoob || !(myt < t_exit) || !(steps + lane + 1 < kMaxSteps);
         const unsigned stop = __ballot_sync(kFull, last);
@@ -285,19 +289,19 @@ k_occ_samples_in_occupied(int nr_rays, GridGeom g, const float* __restrict__ ori
             while (true) {
                 float myt = 0.f;
                 uint64_t myrng = 0;
-                int myv2 = 0;
-                bool myoob2 = false;
                 float tw = t;
 #pragma unroll 4
                 for (int k = 0; k < 32; k++) {
+                    if (lane == k) { myt = tw; myrng = rng.state; }
                     const float tk = clampf(tw, t_start, t_exit);
                     const float qx = __fmaf_rn(r.dx, tk, r.ox), qy = __fmaf_rn(r.dy, tk, r.oy), qz = __fmaf_rn(r.dz, tk, r.oz);
-                    const int v2 = pos_to_voxel_t<kInvMul>(qx, qy, qz, g, Vf);
-                    if (lane == k) { myt = tw; myrng = rng.state; myv2 = v2; myoob2 = (v2 >= nv || v2 < 0); }
                     float delta = dda_step_s(qx, qy, qz, hsx, hsy, hsz, r.ix, r.iy, r.iz, Vf, inv_V);
                     if (jitter) delta = __fmaf_rn(rng.next_float(), spacing, delta);
                     tw = __fadd_rn(__fadd_rn(tk, delta), eps);
                 }
+                const float mtk = clampf(myt, t_start, t_exit);
+                const int myv2 = pos_to_voxel_t<kInvMul>(__fmaf_rn(r.dx, mtk, r.ox), __fmaf_rn(r.dy, mtk, r.oy), __fmaf_rn(r.dz, mtk, r.oz), g, Vf);
+                const bool myoob2 = (myv2 >= nv || myv2 < 0);
                 const bool in2 = (myt < t_exit) && (steps + lane < kMaxSteps);
                 const bool occ2 = in2 && !myoob2 && __ldg(occ + myv2);
                 const unsigned stop2 = __ballot_sync(kFull, !in2 || myoob2 || occ2);
@@ -639,51 +643,6 @@ __global__ void __launch_bounds__(kThreads) k_per_sample_ray_idx(int nr_rays, in
 // ------------------------------------------------------------------------------------------------ SH + ray generation
 // Real spherical harmonics up to degree 7 (PermutoSDFGPU.cuh:275-365). Channel c of sample i is evaluated by thread
 // (i, c-group): the polynomial table is the standard one; outputs are written as a coalesced [N, degree^2] block.
-__device__ __forceinline__ void sh_eval(float x, float y, float z, int degree, float* o) {
-    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
-    o[0] = 0.28209479177387814f;
-    if (degree <= 1) return;
-    const float c1 = 0.48860251190291987f;
-    o[1] = -c1 * y; o[2] = c1 * z; o[3] = -c1 * x;
-    if (degree <= 2) return;
-    const float c2 = 1.0925484305920792f;
-    o[4] = c2 * xy; o[5] = -c2 * yz; o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f; o[7] = -c2 * xz;
-    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
-    if (degree <= 3) return;
-    const float c3a = 0.59004358992664352f, c3b = 0.45704579946446572f;
-    o[9] = c3a * y * (-3.0f * x2 + y2); o[10] = 2.8906114426405538f * xy * z; o[11] = c3b * y * (1.0f - 5.0f * z2);
-    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f); o[13] = c3b * x * (1.0f - 5.0f * z2);
-    o[14] = 1.4453057213202769f * z * (x2 - y2); o[15] = c3a * x * (-x2 + 3.0f * y2);
-    if (degree <= 4) return;
-    const float x4 = x2 * x2, y4 = y2 * y2, z4 = z2 * z2;
-    const float c4a = 1.7701307697799304f, c4b = 0.66904654355728921f;
-    o[16] = 2.5033429417967046f * xy * (x2 - y2); o[17] = c4a * yz * (-3.0f * x2 + y2);
-    o[18] = 0.94617469575756008f * xy * (7.0f * z2 - 1.0f); o[19] = c4b * yz * (3.0f - 7.0f * z2);
-    o[20] = -3.1735664074561294f * z2 + 3.7024941420321507f * z4 + 0.31735664074561293f;
-    o[21] = c4b * xz * (3.0f - 7.0f * z2); o[22] = 0.47308734787878004f * (x2 - y2) * (7.0f * z2 - 1.0f);
-    o[23] = c4a * xz * (-x2 + 3.0f * y2);
-    o[24] = -3.7550144126950569f * x2 * y2 + 0.62583573544917614f * x4 + 0.62583573544917614f * y4;
-    if (degree <= 5) return;
-    const float c5a = 0.65638205684017015f, c5b = 0.48923829943525038f, c5c = 0.45294665119569694f;
-    o[25] = c5a * y * (10.0f * x2 * y2 - 5.0f * x4 - y4); o[26] = 8.3026492595241645f * xy * z * (x2 - y2);
-    o[27] = -c5b * y * (3.0f * x2 - y2) * (9.0f * z2 - 1.0f); o[28] = 4.7935367849733241f * xy * z * (3.0f * z2 - 1.0f);
-    o[29] = c5c * y * (14.0f * z2 - 21.0f * z4 - 1.0f); o[30] = 0.1169503224534236f * z * (-70.0f * z2 + 63.0f * z4 + 15.0f);
-    o[31] = c5c * x * (14.0f * z2 - 21.0f * z4 - 1.0f); o[32] = 2.3967683924866621f * z * (x2 - y2) * (3.0f * z2 - 1.0f);
-    o[33] = -c5b * x * (x2 - 3.0f * y2) * (9.0f * z2 - 1.0f); o[34] = 2.0756623148810411f * z * (-6.0f * x2 * y2 + x4 + y4);
-    o[35] = c5a * x * (10.0f * x2 * y2 - x4 - 5.0f * y4);
-    if (degree <= 6) return;
-    const float x6 = x4 * x2, y6 = y4 * y2, z6 = z4 * z2;
-    const float c6a = 2.3666191622317521f, c6b = 0.92120525951492349f, c6c = 0.58262136251873131f;
-    o[36] = 1.3663682103838286f * xy * (-10.0f * x2 * y2 + 3.0f * x4 + 3.0f * y4); o[37] = c6a * yz * (10.0f * x2 * y2 - 5.0f * x4 - y4);
-    o[38] = 2.0182596029148963f * xy * (x2 - y2) * (11.0f * z2 - 1.0f); o[39] = -c6b * yz * (3.0f * x2 - y2) * (11.0f * z2 - 3.0f);
-    o[40] = c6b * xy * (-18.0f * z2 + 33.0f * z4 + 1.0f); o[41] = c6c * yz * (30.0f * z2 - 33.0f * z4 - 5.0f);
-    o[42] = 6.6747662381009842f * z2 - 20.024298714302954f * z4 + 14.684485723822165f * z6 - 0.31784601133814211f;
-    o[43] = c6c * xz * (30.0f * z2 - 33.0f * z4 - 5.0f);
-    o[44] = 0.46060262975746175f * (x2 - y2) * (11.0f * z2 * (3.0f * z2 - 1.0f) - 7.0f * z2 + 1.0f);
-    o[45] = -c6b * xz * (x2 - 3.0f * y2) * (11.0f * z2 - 3.0f); o[46] = 0.50456490072872406f * (11.0f * z2 - 1.0f) * (-6.0f * x2 * y2 + x4 + y4);
-    o[47] = c6a * xz * (10.0f * x2 * y2 - x4 - 5.0f * y4);
-    o[48] = 10.247761577878714f * x2 * y4 - 10.247761577878714f * x4 * y2 + 0.6831841051919143f * x6 - 0.6831841051919143f * y6;
-}
 template <int DEG>
 __global__ void __launch_bounds__(128) k_spherical_harmonics(int n, const float* __restrict__ dirs, float* __restrict__ out) {
     constexpr int C = DEG * DEG;

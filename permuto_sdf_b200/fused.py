@@ -274,3 +274,103 @@ class CalibSigmoidFn(torch.autograd.Function):
         gbs = torch.zeros_like(wd) if need_p else None
         call("psdf_calib_sigmoid_backward", *ctx.rsp, xc, out, g.contiguous(), img if wd is not None else None, wd, ctx.fixed, gx, gwd, gbs)
         return gx, None, None, gwd, gbs, None
+
+
+# ================================================================================================ fused colour network
+class FusedRGB:
+    """models.RGB on the tensor cores (csrc/fused_rgb.cu, fused_rgb_bwd.cu): encoding + SH + normal + geom -> Lipschitz MLP.
+    The Lipschitz normalisation of the weights stays a (differentiable) per-layer kernel outside; the fused kernels see the
+    normalised matrices W_eff through a packed operand blob."""
+
+    def __init__(self, model_rgb):
+        self.model = model_rgb
+        enc = model_rgb.encoding
+        self.layers = list(model_rgb.mlp.layers)
+        if len(self.layers) != 4 or self.layers[3].out_features != 3 or not model_rgb.mlp.last_layer_linear:
+            raise RuntimeError("FusedRGB supports the 4-layer colour MLP of the reference (models.py:330-340)")
+        if enc.pos_dim != 3 or enc.nr_feat_per_level != 2 or not enc.concat_points or enc.nr_levels % 4 != 0:
+            raise RuntimeError("FusedRGB needs pos_dim 3, 2 features per level, concat_points and nr_levels % 4 == 0")
+        self.in_dim = self.layers[0].in_features
+        self.h = [l.out_features for l in self.layers[:3]]
+        if self.in_dim != enc.output_dims() + 25 + 3 + 32 or self.in_dim > 128 or any(h > 128 or h % 16 for h in self.h):
+            raise RuntimeError("unsupported colour MLP shape for the fused kernel")
+        lib = load_library()
+        self.blob = torch.empty(int(lib.psdf_rgb_mlp_blob_bytes(self.in_dim, *self.h, 3)), dtype=torch.uint8, device=enc.lattice_values.device)
+
+    def normalized_weights(self):
+        mlp = self.model.mlp
+        return [LipschitzNormFn.apply(l.weight, mlp.lipshitz_bound_per_layer[i]) for i, l in enumerate(self.layers)]
+
+    def pack(self, w_eff):
+        l = self.layers
+        call("psdf_rgb_mlp_pack", self.in_dim, *self.h, 3, w_eff[0].detach(), l[0].bias.detach(), w_eff[1].detach(), l[1].bias.detach(),
+             w_eff[2].detach(), l[2].bias.detach(), w_eff[3].detach(), l[3].bias.detach(), self.blob)
+
+    def _window(self, iter_nr):
+        from .models import map_range_val
+        m = self.model
+        m.last_iter_nr = int(iter_nr)
+        return m.c2f(map_range_val(iter_nr, 0.0, m.nr_iters_for_c2f, 0.3, 1.0)).view(-1).contiguous()
+
+    @torch.no_grad()
+    def __call__(self, points, samples_dirs, sdf_gradients, geom_feat, iter_nr):
+        """-> linear colour [N,3] (before calibration / sigmoid), no autograd"""
+        self.pack(self.normalized_weights())
+        enc = self.model.encoding
+        N = points.shape[0]
+        out = torch.empty(N, 3, device=points.device)
+        call("psdf_rgb_fused_forward", N, enc.nr_levels, enc.capacity, points.contiguous(), samples_dirs.contiguous(),
+             sdf_gradients.contiguous(), geom_feat.contiguous(), geom_feat.shape[1], enc.lattice_values.detach(), enc.scale_factor,
+             enc.shift_tensor(), self._window(iter_nr), enc.concat_points_scaling, *self.h, self.blob, out)
+        return out
+
+
+class _FusedRGBTrainFn(torch.autograd.Function):
+    """forward: psdf_rgb_fused_forward; backward: psdf_rgb_fused_backward (reverse sweep + tensor-core dW). Differentiable wrt the
+    hash table, the (normalised) weights, the biases, the sdf gradients and the geometric feature; not wrt points / view dirs."""
+
+    @staticmethod
+    def forward(ctx, points, dirs, sdf_grad, geom, lattice, w0, b0, w1, b1, w2, b2, w3, b3, window, fr):
+        enc = fr.model.encoding
+        fr.pack([w0, w1, w2, w3])
+        N = points.shape[0]
+        out = torch.empty(N, 3, device=points.device)
+        sg, gm = sdf_grad.detach().contiguous(), geom.detach().contiguous()
+        call("psdf_rgb_fused_forward", N, enc.nr_levels, enc.capacity, points, dirs, sg, gm, gm.shape[1], lattice.detach(), enc.scale_factor,
+             enc.shift_tensor(), window, enc.concat_points_scaling, *fr.h, fr.blob, out)
+        ctx.fr = fr
+        ctx.save_for_backward(points, dirs, sg, gm, lattice, window)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        fr = ctx.fr
+        points, dirs, sg, gm, lattice, window = ctx.saved_tensors
+        enc = fr.model.encoding
+        N = points.shape[0]
+        dev = points.device
+        dims = [fr.in_dim] + fr.h + [3]
+        gW = [torch.zeros(dims[l + 1], dims[l], device=dev) for l in range(4)]
+        gb = [torch.zeros(dims[l + 1], device=dev) for l in range(4)]
+        g_sg = torch.zeros_like(sg)
+        g_gm = torch.zeros_like(gm)
+        ws = torch.empty(int(load_library().psdf_rgb_fused_backward_workspace_bytes(N)), dtype=torch.uint8, device=dev)
+        in_place = getattr(enc, "grad_in_place", False) and lattice.grad is not None and lattice.grad.is_contiguous()
+        g_lat = lattice.grad if in_place else torch.zeros_like(lattice)
+        # the packed blob still holds this iteration's weights (pack happens in forward, one forward per iteration)
+        call("psdf_rgb_fused_backward", N, enc.nr_levels, enc.capacity, points, dirs, sg, gm, gm.shape[1], lattice.detach(), enc.scale_factor,
+             enc.shift_tensor(), window, enc.concat_points_scaling, *fr.h, fr.blob, g_out.contiguous(), g_lat, g_sg, g_gm, ws, gW[0], gW[1],
+             gW[2], gW[3], gb[0], gb[1], gb[2], gb[3])
+        return (None, None, g_sg, g_gm, None if in_place else g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
+
+
+def _fused_rgb_train_forward(self, points, samples_dirs, sdf_gradients, geom_feat, iter_nr):
+    """differentiable linear colour [N,3]: Lipschitz normalisation (kernel pair per layer) -> fused forward / backward"""
+    w = self.normalized_weights()
+    l = self.layers
+    return _FusedRGBTrainFn.apply(points.detach().contiguous(), samples_dirs.detach().contiguous(), sdf_gradients, geom_feat,
+                                  self.model.encoding.lattice_values, w[0], l[0].bias, w[1], l[1].bias, w[2], l[2].bias, w[3], l[3].bias,
+                                  self._window(iter_nr), self)
+
+
+FusedRGB.train_forward = _fused_rgb_train_forward

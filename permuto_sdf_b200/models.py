@@ -266,11 +266,17 @@ class RGB(torch.nn.Module):
         self.nr_iters_for_c2f = nr_iters_for_c2f
         self.last_iter_nr = sys.maxsize
         self.fused_head = True
+        self.fused = None
 
     def forward(self, points, samples_dirs, sdf_gradients, geom_feat, iter_nr, model_colorcal=None, img_indices=None,
                 ray_start_end_idx=None):
         assert points.shape[1] == self.in_channels, "points should be N x in_channels"
         self.last_iter_nr = int(iter_nr)
+        if self.fused is not None and points.is_cuda:
+            # encoding + SH + normal + geom -> Lipschitz MLP in the fused tensor-core kernels (csrc/fused_rgb.cu, fused_rgb_bwd.cu)
+            x = self.fused.train_forward(points, samples_dirs, sdf_gradients, geom_feat, iter_nr) if torch.is_grad_enabled() else \
+                self.fused(points, samples_dirs, sdf_gradients, geom_feat, iter_nr)
+            return self._head(x, model_colorcal, img_indices, ray_start_end_idx)
         window = self.c2f(map_range_val(iter_nr, 0.0, self.nr_iters_for_c2f, 0.3, 1.0))
         feat = self.encoding(points, window.view(-1))
         with torch.no_grad():
@@ -278,6 +284,15 @@ class RGB(torch.nn.Module):
         normals = F.normalize(sdf_gradients.view(-1, 3), dim=1)
         x = torch.cat([feat, dirs_enc, normals, geom_feat], 1)
         x = self.mlp(x)
+        return self._head(x, model_colorcal, img_indices, ray_start_end_idx)
+
+    def enable_fused(self):
+        """route forward / backward through the fused colour-network kernels"""
+        from .fused import FusedRGB
+        self.fused = FusedRGB(self)
+        return self.fused
+
+    def _head(self, x, model_colorcal, img_indices, ray_start_end_idx):
         if self.fused_head and x.is_cuda and ray_start_end_idx is not None:
             # colour calibration + sigmoid in one kernel each way (csrc/rgb_misc.cu)
             from .fused import CalibSigmoidFn

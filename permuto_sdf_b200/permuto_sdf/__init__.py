@@ -92,13 +92,23 @@ class RaySamplesPacked:
         self.m_nr_rays = int(nr_rays)
         self.max_nr_samples = int(nr_samples_maximum)
         M = self.max_nr_samples
-        alloc = torch.zeros if zero else torch.empty
         self.is_compact = False
         self.cur_nr_samples = torch.zeros(1, dtype=torch.int32, device=d)
-        self.samples_pos = alloc(M, 3, device=d)
-        self.samples_dirs = alloc(M, 3, device=d)
-        self.samples_z = alloc(M, 1, device=d)
-        self.samples_dt = alloc(M, 1, device=d)
+        if zero:
+            # one zero-filled arena (a single memset) carved into the per-sample arrays; offsets keep 16-byte alignment
+            Mp = (M + 3) // 4 * 4
+            arena = torch.zeros(9 * Mp, device=d)
+            self.samples_pos = arena[0:3 * M].view(M, 3)
+            self.samples_dirs = arena[3 * Mp:3 * Mp + 3 * M].view(M, 3)
+            self.samples_z = arena[6 * Mp:6 * Mp + M].view(M, 1)
+            self.samples_dt = arena[7 * Mp:7 * Mp + M].view(M, 1)
+            self._zero_sdf = arena[8 * Mp:8 * Mp + M].view(M, 1)
+        else:
+            self.samples_pos = torch.empty(M, 3, device=d)
+            self.samples_dirs = torch.empty(M, 3, device=d)
+            self.samples_z = torch.empty(M, 1, device=d)
+            self.samples_dt = torch.empty(M, 1, device=d)
+            self._zero_sdf = None
         self._samples_pos_4d = None   # allocated on first use (only background containers need it)
         self._samples_sdf = None
         self.ray_fixed_dt = torch.empty(self.m_nr_rays, 1, device=d)
@@ -158,7 +168,7 @@ class RaySamplesPacked:
             if self._samples_pos_4d is not None:
                 out._samples_pos_4d = torch.zeros(exact, 4, device=d)
             if self._samples_sdf is not None:
-                out._samples_sdf = torch.zeros(exact, 1, device=d)
+                out._samples_sdf = out._zero_sdf
         else:
             out.cur_nr_samples.fill_(exact)
         if R > 0:
@@ -529,7 +539,7 @@ class VolumeRendering:
         comb = RaySamplesPacked(R, max(c_max, 1), zero=RaySamplesPacked.static_capacity)
         comb.is_compact = True          # the merge writes ray after ray at the scanned offsets
         if RaySamplesPacked.static_capacity and rsp.has_sdf:
-            comb._samples_sdf = torch.zeros(max(c_max, 1), 1, device=rsp.samples_z.device)
+            comb._samples_sdf = comb._zero_sdf
         comb.has_sdf = rsp.has_sdf
         nblocks = (max(R, 1) + 1023) // 1024
         ws = torch.empty(R + nblocks + 1, dtype=torch.int32, device=rsp.samples_z.device)

@@ -250,6 +250,10 @@ class Trainer:
             self.model_sdf.enable_fused_inference()
             if fused_training:
                 self.model_sdf.enable_fused_training()
+                try:                                  # colour network on the tensor cores when its shape fits the fused kernels
+                    self.model_rgb.enable_fused()
+                except RuntimeError:
+                    pass
         groups = [{"params": list(self.model_sdf.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_sdf"}]
         if self.model_bg is not None:
             groups.append({"params": list(self.model_bg.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_bg"})

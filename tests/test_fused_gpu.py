@@ -153,3 +153,75 @@ def test_umma_transposed_gemm_weight_gradient_layout(cuda, M, N):
     with open("gpurun_out/umma_m64_layout.txt", "a") as f:
         f.write("M=%d N=%d accumulator row -> TMEM lane: %s\n" % (M, N, lanes))
     assert lanes == list(range(M)) or lanes == [(m // 16) * 32 + (m % 16) for m in range(M)], lanes
+
+
+@pytest.mark.parametrize("L,N,it", [(16, 5000, 20000), (8, 129, 0), (16, 65536, 20000)])
+def test_fused_rgb_forward_matches_model(cuda, L, N, it):
+    """fused colour network (encoding + SH + normal + geom -> Lipschitz MLP on tcgen05) against the modular RGB model"""
+    from permuto_sdf import Sphere
+    from permuto_sdf_b200.fused import FusedRGB
+    from permuto_sdf_b200.models import RGB
+    torch.manual_seed(L + N)
+    m = RGB(3, Sphere(0.5, [0, 0, 0]), 32, 1, nr_levels=L, capacity=2 ** 16).to("cuda")
+    with torch.no_grad():
+        m.encoding.lattice_values.normal_(0, 0.3)
+        for l in m.mlp.layers:
+            l.bias.normal_(0, 0.1)
+        m.mlp.lipshitz_bound_per_layer[1].fill_(1.0)          # make the Lipschitz clamp active on one layer
+    pts = (torch.rand(N, 3, device="cuda") - 0.5) * 0.8
+    dirs = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda"), dim=-1)
+    grads = torch.randn(N, 3, device="cuda") * 2.0
+    geom = torch.randn(N, 32, device="cuda")
+    with torch.no_grad():
+        m.fused_head = False
+        want = m(pts, dirs, grads, geom, it)                 # sigmoid(MLP(...))
+        x = FusedRGB(m)(pts, dirs, grads, geom, it)
+    got = torch.sigmoid(x)
+    assert float((got - want).abs().max()) < 1e-4, float((got - want).abs().max())
+    # and on the linear output itself, relative to its scale
+    want_lin = torch.logit(want.double().clamp(1e-9, 1 - 1e-9)).float()
+    assert float((x - want_lin).abs().max() / want_lin.abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize("L,N,it", [(16, 3000, 20000), (8, 129, 0), (16, 40000, 20000)])
+def test_fused_rgb_training_gradients_match_autograd(cuda, L, N, it):
+    """fused colour-network backward (reverse sweep + tensor-core dW + lattice scatter + normal / geom gradients) against autograd
+    through the modular RGB model"""
+    from permuto_sdf import Sphere
+    from permuto_sdf_b200.models import RGB
+    torch.manual_seed(L * 7 + N)
+    m = RGB(3, Sphere(0.5, [0, 0, 0]), 32, 1, nr_levels=L, capacity=2 ** 14).to("cuda")
+    with torch.no_grad():
+        m.encoding.lattice_values.normal_(0, 0.3)
+        for l in m.mlp.layers:
+            l.bias.normal_(0, 0.1)
+        m.mlp.lipshitz_bound_per_layer[1].fill_(1.0)
+    pts = (torch.rand(N, 3, device="cuda") - 0.5) * 0.8
+    dirs = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda"), dim=-1)
+    grads0 = torch.randn(N, 3, device="cuda") * 2.0
+    geom0 = torch.randn(N, 32, device="cuda")
+    coef = torch.randn(N, 3, device="cuda")
+    m.fused_head = False
+    res = {}
+    for mode in ("modular", "fused"):
+        if mode == "fused":
+            m.enable_fused()
+        m.zero_grad()
+        g = grads0.clone().requires_grad_(True)
+        f = geom0.clone().requires_grad_(True)
+        out = m(pts, dirs, g, f, it)                      # sigmoid(MLP(...)), no calibration
+        loss = (out * coef).sum() + (out ** 2).sum()
+        loss.backward()
+        res[mode] = dict(loss=float(loss), g=g.grad.clone(), f=f.grad.clone(), lat=m.encoding.lattice_values.grad.clone(),
+                         W=[l.weight.grad.clone() for l in m.mlp.layers], b=[l.bias.grad.clone() for l in m.mlp.layers],
+                         c=[c.grad.clone() for c in m.mlp.lipshitz_bound_per_layer])
+    a, b = res["fused"], res["modular"]
+    rel = lambda x, y: float((x - y).abs().max() / (y.abs().max() + 1e-20))
+    assert abs(a["loss"] - b["loss"]) < 1e-4 * abs(b["loss"])
+    assert rel(a["g"], b["g"]) < 1e-3, ("sdf gradient", rel(a["g"], b["g"]))
+    assert rel(a["f"], b["f"]) < 1e-3, ("geom", rel(a["f"], b["f"]))
+    assert rel(a["lat"], b["lat"]) < 1e-3, ("lattice", rel(a["lat"], b["lat"]))
+    for l in range(4):
+        assert rel(a["W"][l], b["W"][l]) < 1e-3, ("W", l, rel(a["W"][l], b["W"][l]))
+        assert rel(a["b"][l], b["b"][l]) < 1e-3, ("b", l, rel(a["b"][l], b["b"][l]))
+        assert float((a["c"][l] - b["c"][l]).abs().max()) < 1e-3 * max(1e-6, float(b["c"][l].abs().max())) + 1e-7, ("c", l)
