@@ -121,6 +121,13 @@ int psdf_vr_importance_sample(PSDF_RSP, const float* origins, const float* dirs,
                               const float* cdf, int nr_imp, uint64_t rng_state, uint64_t rng_inc, int jitter, float* o_pos,
                               float* o_dirs, float* o_z, void* stream);
 long long psdf_vr_combine_workspace_bytes(int nr_rays);
+/* one round of importance_sampling_sdf_model (permuto_sdf_py/utils/sdf_utils.py): sdf2alpha -> clip -> cumprod(1 - alpha + 1e-7) ->
+ * weights -> per-ray normalisation (clamp 1e-6) -> cdf -> importance_sample, one launch, bit-identical to the separate calls.
+ * cdf [N] is scratch + output (the per-ray exclusive cdf). */
+int psdf_vr_importance_round(PSDF_RSP, const float* origins, const float* dirs, const float* ray_fixed_dt, const float* samples_dt,
+                             const float* samples_z, const float* sdf, float inv_s, int dynamic_inv_s, float inv_s_multiplier, int nr_imp,
+                             uint64_t rng_state, uint64_t rng_inc, int jitter, float* cdf, float* o_pos, float* o_dirs, float* o_z,
+                             void* stream);
 int psdf_vr_combine_uniform_samples_with_imp(PSDF_RSP, const float* origins, const float* dirs, const float* t_exit,
                                              const float* u_fixed_dt, const float* u_z, const float* u_sdf, int u_has_sdf,
                                              int imp_n, const float* i_z, const float* i_sdf, int i_has_sdf, int c_max,
@@ -177,6 +184,17 @@ int psdf_calib_sigmoid_forward(PSDF_RSP, const float* x, const int* img_idx, con
 int psdf_calib_sigmoid_backward(PSDF_RSP, const float* x, const float* out, const float* grad_out, const int* img_idx,
                                 const float* weight_delta, int fixed_img, float* grad_x, float* grad_weight_delta, float* grad_bias,
                                 void* stream);
+
+/* Curvature loss of SDF.get_sdf_and_curvature_1d_precomputed_gradient_normal_based (models.py:261-294): shifted sample positions
+ * points + eps * cross(normalize(sdf_grad), normalize(rand_dirs)); curvature [n] = acos(clamp(n . n_shifted)) / pi (rows >=
+ * nr_valid_dev[0] give 0; nr_valid_dev may be NULL) with loss_sum [1] += their sum; backward of  g_loss * scale * mean-or-sum:
+ * the sum is divided by max(nr_valid, 1) when nr_valid_dev is given. */
+int psdf_curvature_shift_points(int n, const float* points, const float* sdf_grad, const float* rand_dirs, float eps, float* out,
+                                void* stream);
+int psdf_curvature_loss_forward(int n, const float* sdf_grad, const float* sdf_grad_shifted, const int* nr_valid_dev, float* curvature,
+                                float* loss_sum, void* stream);
+int psdf_curvature_loss_backward(int n, const float* sdf_grad, const float* sdf_grad_shifted, const int* nr_valid_dev,
+                                 const float* g_loss_dev, float scale, float* grad_sdf_grad, float* grad_sdf_grad_shifted, void* stream);
 
 /* ---------------------------------------------------------------- PermutoSDF statics (include/permuto_sdf/PermutoSDF.cuh:46-55) */
 int psdf_spherical_harmonics(int n, int degree, const float* dirs, float* out, void* stream);

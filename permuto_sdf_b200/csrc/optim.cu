@@ -23,23 +23,37 @@ k_adamw(long long n, float* __restrict__ p, float* __restrict__ g, float* __rest
     }
     const float decay = 1.0f - lr * weight_decay;
     const float step_size = lr / bias_c1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 P = reinterpret_cast<float4*>(p)[i], G = reinterpret_cast<float4*>(g)[i];
-        float4 M = reinterpret_cast<float4*>(m)[i], V = reinterpret_cast<float4*>(v)[i];
-        float* pp = &P.x; float* gg = &G.x; float* mm = &M.x; float* vv = &V.x;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float gr = gg[k] * grad_scale;
-            float pk = pp[k] * decay;
-            mm[k] = beta1 * mm[k] + (1.0f - beta1) * gr;
-            vv[k] = beta2 * vv[k] + (1.0f - beta2) * gr * gr;
-            float denom = sqrtf(vv[k]) / bias_c2_sqrt + eps;
-            pp[k] = pk - step_size * (mm[k] / denom);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // two independent float4 quadruples per thread and iteration: 8 x 16-byte loads in flight before the first use
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n4; i0 += 2 * stride) {
+        const long long i1 = i0 + stride;
+        const bool two = i1 < n4;
+        float4 P[2], G[2], M[2], V[2];
+        P[0] = reinterpret_cast<float4*>(p)[i0]; G[0] = reinterpret_cast<float4*>(g)[i0];
+        M[0] = reinterpret_cast<float4*>(m)[i0]; V[0] = reinterpret_cast<float4*>(v)[i0];
+        if (two) {
+            P[1] = reinterpret_cast<float4*>(p)[i1]; G[1] = reinterpret_cast<float4*>(g)[i1];
+            M[1] = reinterpret_cast<float4*>(m)[i1]; V[1] = reinterpret_cast<float4*>(v)[i1];
         }
-        reinterpret_cast<float4*>(p)[i] = P;
-        reinterpret_cast<float4*>(m)[i] = M;
-        reinterpret_cast<float4*>(v)[i] = V;
-        if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            if (q == 1 && !two) break;
+            float* pp = &P[q].x; float* gg = &G[q].x; float* mm = &M[q].x; float* vv = &V[q].x;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float gr = gg[k] * grad_scale;
+                float pk = pp[k] * decay;
+                mm[k] = beta1 * mm[k] + (1.0f - beta1) * gr;
+                vv[k] = beta2 * vv[k] + (1.0f - beta2) * gr * gr;
+                float denom = sqrtf(vv[k]) / bias_c2_sqrt + eps;
+                pp[k] = pk - step_size * (mm[k] / denom);
+            }
+            const long long i = q ? i1 : i0;
+            reinterpret_cast<float4*>(p)[i] = P[q];
+            reinterpret_cast<float4*>(m)[i] = M[q];
+            reinterpret_cast<float4*>(v)[i] = V[q];
+            if (zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     // tail
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {

@@ -163,3 +163,103 @@ int psdf_calib_sigmoid_backward(int nr_rays, int max_nr_samples, const int* ray_
     return PSDF_OK;
 }
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- curvature loss
+// SDF.get_sdf_and_curvature_1d_precomputed_gradient_normal_based (permuto_sdf_py/models/models.py:261-294):
+//   tangent = cross(normalize(g), normalize(rand));  points_shifted = points + eps * tangent          (k_curv_shift)
+//   curvature = acos(clamp(normalize(g) . normalize(g_shifted), -1 + 1e-6, 1 - 1e-6)) / pi               (k_curv_forward)
+// and the mean of the curvature over the valid samples as the loss term (train_permuto_sdf.py:362-366). The element-wise
+// chain (3 normalisations, cross, dot, clamp, acos, mean) is ~18 launches forward and ~30 backward in PyTorch.
+namespace {
+__device__ __forceinline__ void normalize3(float x, float y, float z, float& nx, float& ny, float& nz, float& inv, bool& ok) {
+    // same operations as F.normalize (no FMA contraction, true divisions): the curvature term is ill-conditioned in these roundings
+    const float n = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+    ok = n > 1e-12f;                               // F.normalize(eps = 1e-12): x / max(|x|, eps)
+    const float den = fmaxf(n, 1e-12f);
+    inv = 1.0f / den;
+    nx = __fdiv_rn(x, den); ny = __fdiv_rn(y, den); nz = __fdiv_rn(z, den);
+}
+__global__ void __launch_bounds__(kThreads)
+k_curv_shift(int n, const float* __restrict__ points, const float* __restrict__ g, const float* __restrict__ rnd, float eps,
+             float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float nx, ny, nz, rx, ry, rz, inv;
+    bool ok;
+    normalize3(g[3 * i], g[3 * i + 1], g[3 * i + 2], nx, ny, nz, inv, ok);
+    normalize3(rnd[3 * i], rnd[3 * i + 1], rnd[3 * i + 2], rx, ry, rz, inv, ok);
+    out[3 * i] = points[3 * i] + (ny * rz - nz * ry) * eps;
+    out[3 * i + 1] = points[3 * i + 1] + (nz * rx - nx * rz) * eps;
+    out[3 * i + 2] = points[3 * i + 2] + (nx * ry - ny * rx) * eps;
+}
+// curv [n] (0 for rows >= *nr_valid_dev) and loss_sum += sum of the valid rows
+__global__ void __launch_bounds__(kThreads)
+k_curv_forward(int n, const float* __restrict__ g, const float* __restrict__ gs, const int* __restrict__ nr_valid_dev,
+               float* __restrict__ curv, float* __restrict__ loss_sum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nv = nr_valid_dev ? min(nr_valid_dev[0], n) : n;
+    float c = 0.0f;
+    if (i < nv) {
+        float ax, ay, az, bx, by, bz, inv;
+        bool ok;
+        normalize3(g[3 * i], g[3 * i + 1], g[3 * i + 2], ax, ay, az, inv, ok);
+        normalize3(gs[3 * i], gs[3 * i + 1], gs[3 * i + 2], bx, by, bz, inv, ok);
+        const float dot = __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+        const float d = fminf(fmaxf(dot, -1.0f + 1e-6f), 1.0f - 1e-6f);
+        c = acosf(d) * 0.3183098861837907f;
+    }
+    if (i < n) curv[i] = c;
+    const float s = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && s != 0.0f) atomicAdd(loss_sum, s);
+}
+// d (scale * sum_valid curv) / d g, d gs ; scale = *g_loss_dev * (by_count ? 1 / max(nr_valid, 1) : 1)
+__global__ void __launch_bounds__(kThreads)
+k_curv_backward(int n, const float* __restrict__ g, const float* __restrict__ gs, const int* __restrict__ nr_valid_dev,
+                const float* __restrict__ g_loss_dev, float scale, float* __restrict__ gg, float* __restrict__ ggs) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nv = nr_valid_dev ? min(nr_valid_dev[0], n) : n;
+    float o[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (i < nv) {
+        float ax, ay, az, bx, by, bz, ia, ib;
+        bool oka, okb;
+        normalize3(g[3 * i], g[3 * i + 1], g[3 * i + 2], ax, ay, az, ia, oka);
+        normalize3(gs[3 * i], gs[3 * i + 1], gs[3 * i + 2], bx, by, bz, ib, okb);
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+        if (d >= -1.0f + 1e-6f && d <= 1.0f - 1e-6f) {          // clamp passes the gradient inside the range (bounds included)
+            const float up = (g_loss_dev ? g_loss_dev[0] : 1.0f) * scale / (float)(nr_valid_dev ? max(nv, 1) : 1);
+            const float k = -up * 0.3183098861837907f / sqrtf(1.0f - d * d);     // d acos(d) / pi
+            // d d / d g = (b - a (a.b)) / |g| when |g| > eps, else b / eps
+            o[0] = k * (oka ? (bx - ax * d) : bx) * ia; o[1] = k * (oka ? (by - ay * d) : by) * ia; o[2] = k * (oka ? (bz - az * d) : bz) * ia;
+            o[3] = k * (okb ? (ax - bx * d) : ax) * ib; o[4] = k * (okb ? (ay - by * d) : ay) * ib; o[5] = k * (okb ? (az - bz * d) : az) * ib;
+        }
+    }
+    gg[3 * i] = o[0]; gg[3 * i + 1] = o[1]; gg[3 * i + 2] = o[2];
+    ggs[3 * i] = o[3]; ggs[3 * i + 1] = o[4]; ggs[3 * i + 2] = o[5];
+}
+}  // namespace
+
+extern "C" {
+int psdf_curvature_shift_points(int n, const float* points, const float* sdf_grad, const float* rand_dirs, float eps, float* out,
+                                void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_curv_shift<<<div_up(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(n, points, sdf_grad, rand_dirs, eps, out);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_curvature_loss_forward(int n, const float* sdf_grad, const float* sdf_grad_shifted, const int* nr_valid_dev, float* curvature,
+                                float* loss_sum, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_curv_forward<<<div_up(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(n, sdf_grad, sdf_grad_shifted, nr_valid_dev, curvature, loss_sum);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_curvature_loss_backward(int n, const float* sdf_grad, const float* sdf_grad_shifted, const int* nr_valid_dev,
+                                 const float* g_loss_dev, float scale, float* grad_sdf_grad, float* grad_sdf_grad_shifted, void* stream) {
+    if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
+    k_curv_backward<<<div_up(n, kThreads), kThreads, 0, (cudaStream_t)stream>>>(n, sdf_grad, sdf_grad_shifted, nr_valid_dev, g_loss_dev, scale,
+                                                                               grad_sdf_grad, grad_sdf_grad_shifted);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+}  // extern "C"

@@ -219,6 +219,112 @@ k_importance_sample(int nr_rays, const float* __restrict__ origins, const float*
     }
 }
 
+// One round of SDF-driven importance sampling (permuto_sdf_py/utils/sdf_utils.py importance_sampling_sdf_model: sdf2alpha ->
+// clip -> cumprod(1 - alpha + 1e-7) -> weights -> per-ray normalisation -> cdf -> importance_sample) in ONE launch. Every
+// intermediate keeps the arithmetic and the left-to-right order of the separate kernels / PyTorch ops it replaces (tests compare
+// bit for bit); `cdf` is both scratch (un-normalised weights) and output.
+__global__ void __launch_bounds__(kThreads)
+k_importance_round(int nr_rays, const float* __restrict__ origins, const float* __restrict__ dirs, int max_nr_samples,
+                   const int* __restrict__ start_end, const float* __restrict__ ray_fixed_dt, const float* __restrict__ dt_, bool equal,
+                   int fixed_n, const float* __restrict__ z, const float* __restrict__ sdf, float inv_s_in, bool dynamic_inv_s,
+                   float inv_s_mult, int nr_imp, Pcg32 rng0, bool jitter, float* __restrict__ cdf, float* __restrict__ o_pos,
+                   float* __restrict__ o_dirs, float* __restrict__ o_z) {
+    rng0.resolve();
+    RAY_PROLOGUE();
+    if (!skip) {
+        float inv_s = inv_s_in;
+        if (dynamic_inv_s) inv_s = map_range(ray_fixed_dt[ray], 0.0001f, 0.01f, 1024.f, 64.f);
+        inv_s = __fmul_rn(inv_s, inv_s_mult);
+        // alpha (k_sdf2alpha + clip) -> transmittance (k_cumprod of 1 - alpha + 1e-7) -> weight alpha * T
+        float T = 1.0f;
+        for (int base = 0; base < rr.n; base += 32) {
+            const int i = base + lane, s = rr.start + i;
+            float a = 0.0f;
+            if (i < rr.n - 1) {
+                const float dt = dt_[s];
+                const float prev = sdf[s], next = sdf[s + 1];
+                const float mid = __fmul_rn(__fadd_rn(prev, next), 0.5f);
+                float cosv = __fdiv_rn(__fsub_rn(next, prev), fmaxf(1e-6f, dt));
+                cosv = clampf(cosv, -1e3f, 0.0f);
+                const float h = __fmul_rn(cosv, dt);
+                const float pe = (float)((double)mid - (double)h * 0.5);
+                const float ne = (float)((double)mid + (double)h * 0.5);
+                const float pc = sigmoid_ref(__fmul_rn(pe, inv_s)), nc = sigmoid_ref(__fmul_rn(ne, inv_s));
+                a = (float)(((double)__fsub_rn(pc, nc) + 1e-6) / ((double)pc + 1e-6));
+            }
+            a = fminf(fmaxf(a, 0.0f), 1.0f);
+            const float b = (i < rr.n) ? __fadd_rn(__fsub_rn(1.0f, a), 1e-7f) : 1.0f;
+            float mine = 1.0f;
+            const int cnt = min(32, rr.n - base);
+            for (int k = 0; k < cnt; k++) {
+                const float bk = __shfl_sync(kFull, b, k);
+                if (lane == k) mine = T;
+                if (base + k < rr.n - 1) T = __fmul_rn(T, bk);
+            }
+            if (i < rr.n) cdf[s] = __fmul_rn(a, mine);
+        }
+        __syncwarp();
+        // per-ray sum in sample order (k_sum1), normalisation by clamp(sum, 1e-6), exclusive cumsum (k_cumsum<true>)
+        float acc = 0.0f;
+        for (int base = 0; base < rr.n; base += 32) {
+            const int i = base + lane;
+            const float v = (i < rr.n) ? cdf[rr.start + i] : 0.0f;
+            const int cnt = min(32, rr.n - base);
+            for (int k = 0; k < cnt; k++) acc = __fadd_rn(acc, __shfl_sync(kFull, v, k));
+        }
+        const float denom = fmaxf(acc, 1e-6f);
+        float run = 0.0f;
+        for (int base = 0; base < rr.n; base += 32) {
+            const int i = base + lane;
+            const float v = (i < rr.n) ? __fdiv_rn(cdf[rr.start + i], denom) : 0.0f;
+            float mine = 0.0f;
+            const int cnt = min(32, rr.n - base);
+            for (int k = 0; k < cnt; k++) {
+                const float vk = __shfl_sync(kFull, v, k);
+                if (lane == k) mine = run;
+                run = __fadd_rn(run, vk);
+            }
+            if (i < rr.n) cdf[rr.start + i] = mine;
+        }
+        __syncwarp();
+    }
+    // importance samples from the cdf (same body as k_importance_sample)
+    const int ist = ray * nr_imp;
+    const float ox = origins[3 * ray], oy = origins[3 * ray + 1], oz = origins[3 * ray + 2];
+    const float dx = dirs[3 * ray], dy = dirs[3 * ray + 1], dz = dirs[3 * ray + 2];
+    const float fixed_dt = ray_fixed_dt[ray];
+    for (int i = lane; i < nr_imp; i += 32) {
+        const int s = ist + i;
+        if (skip) {
+            o_pos[3 * s] = 0; o_pos[3 * s + 1] = 0; o_pos[3 * s + 2] = 0;
+            o_dirs[3 * s] = 0; o_dirs[3 * s + 1] = 0; o_dirs[3 * s + 2] = 0;
+            o_z[s] = -1.0f;
+            continue;
+        }
+        const float du = (float)(1.0 / (double)(nr_imp + 1));
+        float u = __fmaf_rn((float)i, du, du);
+        if (jitter) {
+            Pcg32 rng = rng0;
+            rng.advance((int64_t)(i + 1) * (int64_t)ray + (int64_t)i);
+            const float rnd = rng.next_float();
+            const float mov = (float)((double)du / 2.0);
+            u = __fadd_rn(u, map_range(rnd, 0.0f, 1.0f, -mov, mov));
+        }
+        u = clampf(u, (float)(0.0 + 1e-6), (float)(1.0 - 1e-5));
+        const int imax = cdf_search(cdf, u, rr.start, rr.end - 1);
+        const int imin = max(imax - 1, 0);
+        const float cmax = cdf[imax], cmin = cdf[imin];
+        const float zmax = z[imax], zmin = z[imin];
+        float zi = map_range(u, cmin, cmax, zmin, zmax);
+        float dmin = __fsub_rn(zi, zmin), dmax = __fsub_rn(zmax, zi);
+        if (dmin < dmax) { dmin = fminf(dmin, fixed_dt); zi = __fadd_rn(zmin, dmin); }
+        else { dmax = fminf(dmax, fixed_dt); zi = __fsub_rn(zmax, dmax); }
+        o_pos[3 * s] = __fmaf_rn(zi, dx, ox); o_pos[3 * s + 1] = __fmaf_rn(zi, dy, oy); o_pos[3 * s + 2] = __fmaf_rn(zi, dz, oz);
+        o_dirs[3 * s] = dx; o_dirs[3 * s + 1] = dy; o_dirs[3 * s + 2] = dz;
+        o_z[s] = zi;
+    }
+}
+
 // VolumeRenderingGPU.cuh:950-1131. Two-pointer merge of the uniform and importance samples of one ray.
 // Lane 0 replays the reference's merge decisions into shared memory (source index per output slot), then
 // the whole warp materialises positions / dirs / z / sdf / dt with coalesced stores. Output slots come from
@@ -542,6 +648,18 @@ int psdf_vr_importance_sample(RSP_ARGS, const float* origins, const float* dirs,
     k_importance_sample<<<ray_blocks(nr_rays), kThreads, 0, ST>>>(nr_rays, origins, dirs, max_nr_samples, ray_start_end, ray_fixed_dt,
                                                                  equal != 0, fixed_n, samples_z, cdf, nr_imp,
                                                                  Pcg32(rng_state, rng_inc), jitter != 0, o_pos, o_dirs, o_z);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+int psdf_vr_importance_round(RSP_ARGS, const float* origins, const float* dirs, const float* ray_fixed_dt, const float* samples_dt,
+                             const float* samples_z, const float* sdf, float inv_s, int dynamic_inv_s, float inv_s_multiplier, int nr_imp,
+                             uint64_t rng_state, uint64_t rng_inc, int jitter, float* cdf, float* o_pos, float* o_dirs, float* o_z,
+                             void* stream) {
+    GUARD();
+    k_importance_round<<<ray_blocks(nr_rays), kThreads, 0, ST>>>(nr_rays, origins, dirs, max_nr_samples, ray_start_end, ray_fixed_dt, samples_dt,
+                                                                equal != 0, fixed_n, samples_z, sdf, inv_s, dynamic_inv_s != 0,
+                                                                inv_s_multiplier, nr_imp, Pcg32(rng_state, rng_inc), jitter != 0, cdf, o_pos,
+                                                                o_dirs, o_z);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }

@@ -138,19 +138,27 @@ class _FusedSDFTrainFn(torch.autograd.Function):
         dev = points.device
         dims_k = [fused.in_dim, fused.hidden, fused.hidden, fused.hidden]
         dims_n = [fused.hidden, fused.hidden, fused.hidden, fused.out_dim]
-        gW = [torch.zeros(n, k, device=dev) for n, k in zip(dims_n, dims_k)]
-        gb = [torch.zeros(n, device=dev) for n in dims_n]
         ws = torch.empty(int(load_library().psdf_sdf_fused_backward_workspace_bytes(N)), dtype=torch.uint8, device=dev)
-        # with a flat-buffer optimizer the hash-table gradient is scattered straight into lattice.grad (no 33 MB zero-fill
-        # plus accumulate pass per call); autograd then gets no gradient for the table from this node
-        in_place = getattr(enc, "grad_in_place", False) and lattice.grad is not None and lattice.grad.is_contiguous()
+        # with a flat-buffer optimizer the gradients are accumulated straight into the persistent .grad buffers (hash table:
+        # no 33 MB zero-fill plus accumulate pass per call; MLP: no zero-fills / add_ per tensor); autograd then gets no
+        # gradient for those parameters from this node
+        params = [p for l in fused.lin for p in (l.weight, l.bias)]
+        in_place = getattr(enc, "grad_in_place", False) and lattice.grad is not None and lattice.grad.is_contiguous() and \
+            all(p.grad is not None and p.grad.is_contiguous() for p in params)
+        if in_place:
+            gW, gb = [l.weight.grad for l in fused.lin], [l.bias.grad for l in fused.lin]
+        else:
+            gW = [torch.zeros(n, k, device=dev) for n, k in zip(dims_n, dims_k)]
+            gb = [torch.zeros(n, device=dev) for n in dims_n]
         g_lat = lattice.grad if in_place else torch.zeros_like(lattice)
         c = lambda t: None if t is None else t.contiguous()
         # kernel 1: reverse sweep + lattice scatter + operand-tile spill; kernel 2: dW = zbar^T a on the tensor cores
         call("psdf_sdf_fused_backward", N, enc.nr_levels, enc.capacity, points, lattice.detach(), enc.scale_factor, enc.shift_tensor(), window,
              enc.concat_points_scaling, fused.hidden, fused.out_dim, fused.blob, c(g_sdf), c(g_grad), c(g_geom), g_lat, ws, gW[0], gW[1], gW[2],
              gW[3], gb[0], gb[1], gb[2], gb[3])
-        return (None, None if in_place else g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
+        if in_place:
+            return (None,) * 12
+        return (None, g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
 
 
 # ================================================================================================ NeuS compositing + losses
@@ -350,18 +358,21 @@ class _FusedRGBTrainFn(torch.autograd.Function):
         N = points.shape[0]
         dev = points.device
         dims = [fr.in_dim] + fr.h + [3]
-        gW = [torch.zeros(dims[l + 1], dims[l], device=dev) for l in range(4)]
-        gb = [torch.zeros(dims[l + 1], device=dev) for l in range(4)]
-        g_sg = torch.zeros_like(sg)
-        g_gm = torch.zeros_like(gm)
+        in_place = getattr(enc, "grad_in_place", False) and lattice.grad is not None and lattice.grad.is_contiguous() and \
+            all(l.bias.grad is not None and l.bias.grad.is_contiguous() for l in fr.layers)
+        gW = [torch.zeros(dims[l + 1], dims[l], device=dev) for l in range(4)]      # wrt the normalised weights: flows on through autograd
+        gb = [l.bias.grad for l in fr.layers] if in_place else [torch.zeros(dims[l + 1], device=dev) for l in range(4)]
+        g_sg = torch.empty_like(sg)          # every row is written by the kernel
+        g_gm = torch.empty_like(gm)
         ws = torch.empty(int(load_library().psdf_rgb_fused_backward_workspace_bytes(N)), dtype=torch.uint8, device=dev)
-        in_place = getattr(enc, "grad_in_place", False) and lattice.grad is not None and lattice.grad.is_contiguous()
         g_lat = lattice.grad if in_place else torch.zeros_like(lattice)
         # the packed blob still holds this iteration's weights (pack happens in forward, one forward per iteration)
         call("psdf_rgb_fused_backward", N, enc.nr_levels, enc.capacity, points, dirs, sg, gm, gm.shape[1], lattice.detach(), enc.scale_factor,
              enc.shift_tensor(), window, enc.concat_points_scaling, *fr.h, fr.blob, g_out.contiguous(), g_lat, g_sg, g_gm, ws, gW[0], gW[1],
              gW[2], gW[3], gb[0], gb[1], gb[2], gb[3])
-        return (None, None, g_sg, g_gm, None if in_place else g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
+        if in_place:
+            return (None, None, g_sg, g_gm, None, gW[0], None, gW[1], None, gW[2], None, gW[3], None, None, None)
+        return (None, None, g_sg, g_gm, g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
 
 
 def _fused_rgb_train_forward(self, points, samples_dirs, sdf_gradients, geom_feat, iter_nr):
@@ -374,3 +385,39 @@ def _fused_rgb_train_forward(self, points, samples_dirs, sdf_gradients, geom_fea
 
 
 FusedRGB.train_forward = _fused_rgb_train_forward
+
+
+# ================================================================================================ curvature loss
+class CurvatureLossFn(torch.autograd.Function):
+    """mean over the valid samples of acos(clamp(normalize(g) . normalize(g_shifted))) / pi (models.py:283-294 +
+    train_permuto_sdf.py:362-366), one kernel each way (csrc/rgb_misc.cu). n_dev: device int32 [1] count of valid rows
+    (static-capacity containers) or None (all rows)."""
+
+    @staticmethod
+    def forward(ctx, g, gs, n_dev):
+        gc, gsc = g.detach().contiguous(), gs.detach().contiguous()
+        N = gc.shape[0]
+        curv = torch.empty(N, device=gc.device)
+        total = torch.zeros(1, device=gc.device)
+        call("psdf_curvature_loss_forward", N, gc, gsc, n_dev, curv, total)
+        ctx.save_for_backward(gc, gsc, n_dev)
+        ctx.N = N
+        loss = total / (float(max(N, 1)) if n_dev is None else n_dev.clamp(min=1).float())
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        gc, gsc, n_dev = ctx.saved_tensors
+        gg, ggs = torch.empty_like(gc), torch.empty_like(gsc)
+        call("psdf_curvature_loss_backward", ctx.N, gc, gsc, n_dev, g_loss.reshape(1).contiguous(), 1.0 if n_dev is not None else 1.0 / max(ctx.N, 1),
+             gg, ggs)
+        return gg, ggs, None
+
+
+def curvature_shifted_points(points, sdf_gradients, epsilon=1e-4):
+    """points + eps * cross(normalize(sdf_gradients), normalize(randn)) (models.py:266-273), no autograd (the shifted points only feed
+    a forward whose position gradient is not propagated)"""
+    rnd = torch.randn_like(points)
+    out = torch.empty_like(points)
+    call("psdf_curvature_shift_points", points.shape[0], points.detach().contiguous(), sdf_gradients.detach().contiguous(), rnd, float(epsilon), out)
+    return out

@@ -528,6 +528,25 @@ class VolumeRendering:
         return imp
 
     @staticmethod
+    def importance_round(ray_origins, ray_dirs, rsp, sdf_samples, inv_s, dynamic_inv_s, inv_s_multiplier, nr_importance_samples,
+                         jitter_samples):
+        """sdf2alpha -> clip -> cumprod_alpha2transmittance -> weights -> normalise -> compute_cdf -> importance_sample in one launch
+        (one round of importance_sampling_sdf_model); bit-identical to the separate calls, same generator use"""
+        R = rsp.ray_start_end_idx.shape[0]
+        k = int(nr_importance_samples)
+        imp = RaySamplesPacked(R, R * k)
+        imp.rays_have_equal_nr_of_samples = True
+        imp.fixed_nr_of_samples_per_ray = k
+        cdf = torch.zeros(VolumeRendering._N(rsp), 1, device=rsp.samples_z.device)
+        call("psdf_vr_importance_round", *rsp._rsp(), _f32(ray_origins, "ray_origins", 3), _f32(ray_dirs, "ray_dirs", 3), rsp.ray_fixed_dt,
+             rsp.samples_dt, rsp.samples_z, _f32(sdf_samples, "sdf").reshape(-1, 1), float(inv_s), 1 if dynamic_inv_s else 0,
+             float(inv_s_multiplier), k, *VolumeRendering.m_rng.args(), 1 if jitter_samples else 0, cdf, imp.samples_pos, imp.samples_dirs,
+             imp.samples_z)
+        if jitter_samples:
+            VolumeRendering.m_rng.advance()
+        return imp
+
+    @staticmethod
     def combine_uniform_samples_with_imp(ray_origins, ray_dirs, ray_t_exit, rsp, rsp_imp):
         if not rsp_imp.rays_have_equal_nr_of_samples:
             raise RuntimeError("importance samples are expected to have an equal nr of samples per ray")

@@ -66,7 +66,12 @@ def create_samples(with_mask, hyperparams, ray_origins, ray_dirs, jitter_samples
     return fg, bg
 
 
+FUSED_IMPORTANCE_ROUND = True     # one launch per round (csrc/volrender.cu k_importance_round) instead of 9
+
+
 def _imp_round(rsp, sdf, inv_s, inv_s_multiplier, ray_origins, ray_dirs, nr_imp, jitter):
+    if FUSED_IMPORTANCE_ROUND:
+        return VolumeRendering.importance_round(ray_origins, ray_dirs, rsp, sdf.contiguous(), inv_s, True, inv_s_multiplier, nr_imp, jitter)
     alpha = VolumeRendering.sdf2alpha(rsp, sdf, inv_s, True, inv_s_multiplier).clip(0.0, 1.0)
     T, _ = VolumeRendering.cumprod_alpha2transmittance(rsp, 1 - alpha + 1e-7)
     weights = alpha * T
@@ -309,21 +314,25 @@ class Trainer:
         gw_curv = map_range_val(iter_nr_for_anneal, hp.iter_start_reduce_curv, hp.iter_finish_reduce_curv, 1.0, 0.0)
         loss_curv = torch.zeros((), device=loss.device)
         if iter_nr_for_anneal < hp.iter_finish_reduce_curv and fg.samples_pos.shape[0] != 0:      # <=> gw_curv > 0
-            _, curv = self.model_sdf.get_sdf_and_curvature_1d_precomputed_gradient_normal_based(fg.samples_pos, sdf_gradients,
-                                                                                                iter_nr_for_anneal)
-            if RaySamplesPacked.static_capacity:     # rows past the device-side sample count are padding
-                n_dev = fg.cur_nr_samples
-                valid = (torch.arange(curv.shape[0], device=curv.device, dtype=torch.int32) < n_dev).view(-1, 1)
-                loss_curv = torch.where(valid, curv, torch.zeros_like(curv)).sum() / n_dev.clamp(min=1).float().squeeze(0)
+            if self.fused_render:
+                loss_curv = self.model_sdf.curvature_loss(fg.samples_pos, sdf_gradients, iter_nr_for_anneal,
+                                                          fg.cur_nr_samples if RaySamplesPacked.static_capacity else None)
             else:
-                loss_curv = curv.mean()
+                _, curv = self.model_sdf.get_sdf_and_curvature_1d_precomputed_gradient_normal_based(fg.samples_pos, sdf_gradients,
+                                                                                                    iter_nr_for_anneal)
+                if RaySamplesPacked.static_capacity:     # rows past the device-side sample count are padding
+                    n_dev = fg.cur_nr_samples
+                    valid = (torch.arange(curv.shape[0], device=curv.device, dtype=torch.int32) < n_dev).view(-1, 1)
+                    loss_curv = torch.where(valid, curv, torch.zeros_like(curv)).sum() / n_dev.clamp(min=1).float().squeeze(0)
+                else:
+                    loss_curv = curv.mean()
             loss = loss + loss_curv * hp.curvature_weight * gw_curv
         if hp.use_occupancy_grid:
             off = self.aabb.rand_points_inside(nr_points=1024)
             sdf_rand, _ = self.model_sdf(off, iter_nr_for_anneal)
             loss = loss + torch.exp(-1e2 * torch.abs(sdf_rand)).mean() * hp.offsurface_weight
-        loss_lip = self.model_rgb.mlp.lipshitz_bound_full()
-        if iter_nr_for_anneal >= hp.iter_start_reduce_curv:
+        if iter_nr_for_anneal >= hp.iter_start_reduce_curv:      # the bound is only part of the loss from here on
+            loss_lip = self.model_rgb.mlp.lipshitz_bound_full()
             loss = loss + loss_lip.mean() * hp.lipshitz_weight
         if hp.with_mask and not fused_done:
             loss = loss + F.binary_cross_entropy(weights_sum.clip(1e-3, 1.0 - 1e-3), gt_mask) * hp.mask_weight

@@ -71,3 +71,39 @@ def test_calib_sigmoid_matches_torch(cuda, with_calib):
     if with_calib:
         assert rel(res[0][2], res[1][2]) < 1e-4 and rel(res[0][3], res[1][3]) < 1e-4
         assert float(res[0][2][0].abs().max()) == 0.0, "the fixed-calibration image gets no gradient"
+
+
+@pytest.mark.parametrize("static", [False, True])
+def test_curvature_loss_matches_torch(cuda, static):
+    """fused curvature loss (shifted points, acos of the normal agreement, masked mean; forward + backward) against the PyTorch chain of
+    SDF.get_sdf_and_curvature_1d_precomputed_gradient_normal_based (models.py:261-294)"""
+    import math
+    from permuto_sdf_b200.fused import CurvatureLossFn, curvature_shifted_points
+    torch.manual_seed(3)
+    N, nv = 5000, 4321
+    g0 = torch.randn(N, 3, device="cuda")
+    gs0 = g0 + 0.3 * torch.randn(N, 3, device="cuda")
+    gs0[:50] = g0[:50] * 2.0                                # exactly parallel normals: the clamp region
+    n_dev = torch.tensor([nv], dtype=torch.int32, device="cuda") if static else None
+    res = []
+    for fused in (True, False):
+        g, gs = g0.clone().requires_grad_(True), gs0.clone().requires_grad_(True)
+        if fused:
+            loss = CurvatureLossFn.apply(g, gs, n_dev)
+        else:
+            dot = (F.normalize(g, dim=-1) * F.normalize(gs, dim=-1)).sum(dim=-1, keepdim=True)
+            curv = torch.acos(torch.clamp(dot, -1.0 + 1e-6, 1.0 - 1e-6)) / math.pi
+            loss = curv[:nv].mean() if static else curv.mean()
+        (loss * 3.0).backward()
+        res.append((float(loss), g.grad.clone(), gs.grad.clone()))
+    assert abs(res[0][0] - res[1][0]) < 1e-5 * abs(res[1][0])
+    assert rel(res[0][1], res[1][1]) < 1e-3 and rel(res[0][2], res[1][2]) < 1e-3
+    if static:
+        assert float(res[0][1][nv:].abs().max()) == 0.0
+    # shifted points: eps * unit tangent, orthogonal to the normal
+    p = torch.rand(N, 3, device="cuda")
+    torch.manual_seed(9)
+    sh = curvature_shifted_points(p, g0, 1e-4)
+    d = sh - p
+    assert float((d * F.normalize(g0, dim=-1)).sum(-1).abs().max()) < 3e-7       # tangent to the normal (up to the rounding of p + d)
+    assert float(d.norm(dim=-1).max()) <= 1.01e-4

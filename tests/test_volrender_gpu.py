@@ -208,3 +208,26 @@ def test_importance_resampling(packed, jitter):
             for a, b in [(comb.samples_z, rcomb.z), (comb.samples_dt, rcomb.dt), (comb.samples_pos, rcomb.pos), (comb.samples_sdf, rcomb.sdf)]:
                 assert np.array_equal(N(a)[s:e], N(b)[rs:re]), "merged samples differ from the reference kernel"
     rsp.remove_sdf()
+
+
+@pytest.mark.parametrize("jitter,mult", [(False, 1.0), (True, 2.0)])
+def test_importance_round_equals_separate_calls(packed, jitter, mult):
+    """the fused importance-sampling round (one launch) reproduces the chain of separate kernels + PyTorch glue bit for bit,
+    including the jitter stream of the class-static generator"""
+    import permuto_sdf_b200.train as tr
+    from permuto_sdf import VolumeRendering
+    rsp, o, d = packed["rsp"], packed["o"], packed["d"]
+    torch.manual_seed(4)
+    sdf = (rsp.samples_pos.norm(dim=1, keepdim=True) - 0.3 + 0.01 * torch.randn(rsp.samples_pos.shape[0], 1, device="cuda")).contiguous()
+    state = (VolumeRendering.m_rng.state, VolumeRendering.m_rng.inc)
+    out = {}
+    for fused in (False, True):
+        VolumeRendering.m_rng.state, VolumeRendering.m_rng.inc = state
+        tr.FUSED_IMPORTANCE_ROUND = fused
+        imp = tr._imp_round(rsp, sdf, 512, mult, o, d, 16, jitter)
+        out[fused] = (imp.samples_z.clone(), imp.samples_pos.clone(), imp.samples_dirs.clone(), VolumeRendering.m_rng.state)
+    tr.FUSED_IMPORTANCE_ROUND = True
+    assert out[True][3] == out[False][3]
+    for a, b, name in zip(out[True][:3], out[False][:3], ("z", "pos", "dirs")):
+        assert torch.equal(a, b), name
+    assert float(out[True][0].max()) > 0
