@@ -232,6 +232,16 @@ int psdf_sdf_mlp_pack(int in_dim, int hidden, int out_dim, const float* W0, cons
 int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
                            const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, float* sdf,
                            float* grad, float* geom, void* stream);
+/* Fused sphere tracing (sphere_trace, permuto_sdf_py/utils/sdf_utils.py:120-218): nr_iters iterations of
+ *   sdf = SDF(p); p += dir * sdf * sdf_multiplier; converged |= |sdf| < tresh | left the occupied region / bounding sphere
+ * with advance_sample_to_next_occupied_voxel applied after every step when an occupancy grid is given (occupancy != NULL; else
+ * the bounding-sphere test). One CTA traces 128 rays to the end; pos [N,3] start points, dirs [N,3]; pos_out [N,3], converged [N]
+ * (may be NULL). Bit-identical to the masked Python loop on the per-op kernels. */
+int psdf_sdf_sphere_trace(int N, int L, int T, const float* pos, const float* dirs, const float* lattice, const float* scale_factor,
+                          const float* shift, const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob,
+                          int nr_iters, float sdf_multiplier, float sdf_converged_tresh, const uint8_t* occupancy, int V, float extent,
+                          const float trans[3], float sphere_radius, const float sphere_center[3], float* pos_out, uint8_t* converged,
+                          void* stream);
 /* Training backward of psdf_sdf_fused_forward (double backward of encoding + MLP on the tensor cores, two kernels):
  * upstream gradients g_sdf [N], g_grad [N,3], g_geom [N,out_dim-1] (any may be NULL) -> grad_lattice (+=), weight gradients
  * gW_l [N_l, K_l] (+=) and bias gradients gb_l [N_l] (+=). workspace: psdf_sdf_fused_backward_workspace_bytes(N) bytes of

@@ -185,6 +185,65 @@ __device__ __forceinline__ float half_sign(float d) { return d > 0.0f ? 0.5f : (
 
 __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fmaxf(lo, fminf(x, hi)); }
 
+// march from (px,py,pz) along d until an occupied voxel is hit (position updated to the point inside it) or the grid is left
+// (position updated to the exit point, returns false). Body of advance_sample_to_next_occupied_voxel
+// (OccupancyGridGPU.cuh:817-895); shared by the stand-alone kernel and the fused sphere tracer. If the step budget V*sqrt(3) runs
+// out the position stays where it was and the sample counts as inside, like the reference.
+__device__ __forceinline__ bool occ_advance_to_next_occupied(const GridGeom& g, const uint8_t* __restrict__ occ, float& ox, float& oy, float& oz,
+                                                            float dx, float dy, float dz) {
+    const int nv = g.V * g.V * g.V;
+    const float eps = 1e-6f;
+    const float ix = safe_inv(dx), iy = safe_inv(dy), iz = safe_inv(dz);
+    const double max_steps = (double)g.V * sqrt(3.0);
+    float t = 0;
+    int steps = 0;
+    // The t recurrence does not depend on the occupancy bytes, so it runs kAhead steps ahead of them: each batch costs one load
+    // latency instead of kAhead. Decisions are then taken in march order, exactly as one step at a time would.
+    constexpr int kAhead = 8;
+    while ((double)steps < max_steps) {
+        float bx[kAhead], by[kAhead], bz[kAhead];
+        int bv[kAhead];
+        int m = 0;
+        bool oob_at_m = false;
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) {
+            if (!oob_at_m && (double)(steps + k) < max_steps) {
+                const float px = __fmaf_rn(dx, t, ox), py = __fmaf_rn(dy, t, oy), pz = __fmaf_rn(dz, t, oz);
+                const int v = pos_to_voxel(px, py, pz, g);
+                bx[k] = px; by[k] = py; bz[k] = pz; bv[k] = v;
+                m = k + 1;
+                if (v > (nv - 1) || v < 0) oob_at_m = true;        // this entry ends the march; nothing after it is needed
+                else {
+                    const float dn = dda_step(px, py, pz, dx, dy, dz, ix, iy, iz, g.V);
+                    t = __fadd_rn(__fadd_rn(t, dn), eps);
+                }
+            }
+        }
+        uint8_t bo[kAhead];
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) bo[k] = (k < m && !(oob_at_m && k == m - 1)) ? __ldg(occ + bv[k]) : 0;
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) {
+            if (k < m) {
+                if (oob_at_m && k == m - 1) { ox = bx[k]; oy = by[k]; oz = bz[k]; return false; }
+                if (bo[k]) { ox = bx[k]; oy = by[k]; oz = bz[k]; return true; }
+            }
+        }
+        if (m == 0) break;
+        steps += m;
+    }
+    return true;
+}
+inline GridGeom make_grid_geom(int V, float extent, const float* t) {
+    GridGeom g;
+    g.V = V; g.extent = extent; g.tx = t[0]; g.ty = t[1]; g.tz = t[2];
+    int ex = 0;
+    float m = frexpf(extent, &ex);
+    g.inv_extent = (m == 0.5f) ? 1.0f / extent : 0.0f;      // exact reciprocal only for powers of two
+    g.inv_V = 1.0f / (float)V;
+    return g;
+}
+
 // per-ray sample range, mirrors get_start_end_ray_indices (VolumeRenderingGPU.cuh:30-60)
 struct RayRange { int start, end, n; };
 __device__ __forceinline__ RayRange ray_range(int ray, const int* __restrict__ start_end, bool equal, int fixed_n) {

@@ -218,6 +218,170 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
     if (warp == 0) umma::tmem_dealloc(tmem_base, S * 64);
 }
 
+// ---------------------------------------------------------------------------------------------- fused sphere tracing
+// sphere_trace of the reference (permuto_sdf_py/utils/sdf_utils.py:120-218) is a Python loop: mask the unconverged rays, gather,
+// evaluate the SDF network, step along the ray, advance to the next occupied voxel, scatter back -- ~12 launches and a host sync
+// per iteration. Here one CTA owns 128 rays for the whole trace: positions and converged flags live in shared memory, each
+// iteration is encoder -> 4 tensor-core layers -> step / occupancy advance, the weights stay resident, and a tile stops as soon
+// as its 128 rays have converged. Per ray the arithmetic is the one of the loop (same network evaluation, p + (d * sdf) * mult in
+// separate roundings, same DDA), so the traced points are bit-identical to it.
+struct TraceParams {
+    int nr_iters;
+    float sdf_mult, conv_thresh;
+    int has_occ;            // 1: advance through the occupancy grid, 0: test against the bounding sphere
+    psdf::GridGeom grid;
+    float sph_radius, sph_cx, sph_cy, sph_cz;
+};
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_in, const float* __restrict__ dirs,
+                   const float2* __restrict__ lattice, const float* __restrict__ scale, const float* __restrict__ shift,
+                   const float* __restrict__ window, const uint8_t* __restrict__ blob, const uint8_t* __restrict__ occ,
+                   float* __restrict__ pos_out, uint8_t* __restrict__ converged_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_blob = smem;
+    uint8_t* s_a = smem + P.g.total;                       // {hi, lo} x 16 KB
+    LevelC* lc = reinterpret_cast<LevelC*>(s_a + 2 * kATileBytes);
+    float* s_pos = reinterpret_cast<float*>(lc + 1);       // [128][3]
+    int* s_conv = reinterpret_cast<int*>(s_pos + kTile * 3);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_conv + kTile);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & (kTile - 1), grp = tid >> 7;
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }
+    for (int i = tid; i < P.L * 3; i += kFusedThreads) {
+        lc->scale[(i / 3) * 4 + (i % 3)] = scale[i];
+        lc->shift[(i / 3) * 4 + (i % 3)] = shift ? shift[i] : 0.0f;
+    }
+    for (int i = tid; i < P.L; i += kFusedThreads) lc->window[i] = window ? window[i] : 1.0f;
+    __syncthreads();
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 64);
+    if (tid == 0) {
+        umma::mbar_expect_tx(&bars[0], (uint32_t)P.g.total);
+        umma::bulk_g2s(s_blob, blob, (uint32_t)P.g.total, &bars[0]);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+    umma::mbar_wait(&bars[0], 0);
+    uint32_t mma_phase = 0;
+    const int level_cores = P.L / 4, all_cores = P.g.Kp[0] / 8;
+    const float* bias3 = reinterpret_cast<const float*>(s_blob + P.g.bias[kNL - 1]);
+
+    const int ntiles = (P.N + kTile - 1) / kTile;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int n = tile * kTile + row;
+        const bool valid = n < P.N;
+        if (grp == 0) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) s_pos[row * 3 + i] = valid ? pos_in[(size_t)n * 3 + i] : 0.0f;
+            s_conv[row] = valid ? 0 : 1;
+        }
+        __syncthreads();
+        for (int it = 0; it < Q.nr_iters; it++) {
+            const bool active = s_conv[row] == 0;
+            if (__syncthreads_and(!active)) break;           // every ray of the tile has converged
+            float x[3] = {s_pos[row * 3], s_pos[row * 3 + 1], s_pos[row * 3 + 2]};
+            if (active) {
+                for (int kc = grp; kc < all_cores; kc += kGroups) {
+                    float fv[8];
+                    if (kc < level_cores) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int l = kc * 4 + q;
+                            float cf[3], e[4];
+#pragma unroll
+                            for (int i = 0; i < 3; i++) cf[i] = __fmul_rn(__fadd_rn(x[i], lc->shift[l * 4 + i]), lc->scale[l * 4 + i]);
+                            elevate3(cf, e);
+                            Simplex3 s;
+                            locate3(e, s);
+                            const float2* tab = lattice + (size_t)l * P.T;
+                            float2 v[4];
+#pragma unroll
+                            for (int r = 0; r < 4; r++) v[r] = __ldg(tab + vindex3(s, r, P.cap_mask, (unsigned)P.T));
+                            const float w = lc->window[l];
+                            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                            for (int r = 0; r < 4; r++) { float wr = s.bary[r] * w; a0 = fmaf(v[r].x, wr, a0); a1 = fmaf(v[r].y, wr, a1); }
+                            fv[2 * q] = a0; fv[2 * q + 1] = a1;
+                        }
+                    } else {
+                        const int c0 = 2 * P.L;
+#pragma unroll
+                        for (int i = 0; i < 8; i++) {
+                            int c = kc * 8 + i - c0;
+                            float val = 0.f;
+#pragma unroll
+                            for (int d = 0; d < 3; d++) if (c == d && (c0 + c) < P.in_dim) val = x[d] * P.points_scaling;
+                            fv[i] = val;
+                        }
+                    }
+                    store8(s_a, s_a + kATileBytes, row, kc, fv);
+                }
+            }
+#pragma unroll 1
+            for (int l = 0; l < kNL; l++) {
+                umma::fence_async_smem();
+                umma::fence_before_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    umma::fence_after_sync();
+                    issue_gemm(tmem_base, s_a, s_a + kATileBytes, s_blob + P.g.w_hi[l], s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
+                    umma::commit(&bars[1]);
+                }
+                umma::mbar_wait(&bars[1], mma_phase);
+                mma_phase ^= 1;
+                umma::fence_after_sync();
+                const float* bias = reinterpret_cast<const float*>(s_blob + P.g.bias[l]);
+                const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+                const int c = grp;
+                if (l < kNL - 1) {
+                    if (c < P.g.Np[l] / 16) {
+                        float z[16];
+                        umma::tmem_ld16(trow + c * 16, z);
+                        umma::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) { const float zz = z[i] + bias[c * 16 + i]; z[i] = zz * gelu_eval(zz).cdf; }
+                        store8(s_a, s_a + kATileBytes, row, 2 * c, z);
+                        store8(s_a, s_a + kATileBytes, row, 2 * c + 1, z + 8);
+                    }
+                } else if (grp == 0) {
+                    float z[16];
+                    umma::tmem_ld16(trow, z);
+                    umma::tmem_ld_wait();
+                    if (active) {
+                        const float sdf = z[0] + bias3[0];
+                        const float dx = dirs[(size_t)n * 3], dy = dirs[(size_t)n * 3 + 1], dz = dirs[(size_t)n * 3 + 2];
+                        float px = __fadd_rn(x[0], __fmul_rn(__fmul_rn(dx, sdf), Q.sdf_mult));
+                        float py = __fadd_rn(x[1], __fmul_rn(__fmul_rn(dy, sdf), Q.sdf_mult));
+                        float pz = __fadd_rn(x[2], __fmul_rn(__fmul_rn(dz, sdf), Q.sdf_mult));
+                        const bool newly = fabsf(sdf) < Q.conv_thresh;
+                        bool within;
+                        if (Q.has_occ) within = psdf::occ_advance_to_next_occupied(Q.grid, occ, px, py, pz, dx, dy, dz);
+                        else {
+                            const float qx = __fsub_rn(px, Q.sph_cx), qy = __fsub_rn(py, Q.sph_cy), qz = __fsub_rn(pz, Q.sph_cz);
+                            within = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz))) < Q.sph_radius;
+                        }
+                        s_pos[row * 3] = px; s_pos[row * 3 + 1] = py; s_pos[row * 3 + 2] = pz;
+                        if (newly || !within) s_conv[row] = 1;
+                    }
+                }
+                umma::fence_before_sync();
+            }
+            __syncthreads();      // positions / flags of this iteration visible, TMEM reads done
+        }
+        __syncthreads();
+        if (grp == 0 && valid) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) pos_out[(size_t)n * 3 + i] = s_pos[row * 3 + i];
+            if (converged_out) converged_out[n] = (uint8_t)(s_conv[row] != 0);
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem_base, 64);
+}
+
 // ---------------------------------------------------------------------------------------------- debug GEMM (descriptor check)
 // D[128 x N] = A[128 x K] * B[N x K]^T with the same split/pack/issue/load helpers as the fused kernel.
 __global__ void __launch_bounds__(kTile) k_debug_gemm(int N, int K, const float* __restrict__ A, const float* __restrict__ B,
@@ -350,6 +514,40 @@ __global__ void __launch_bounds__(kTile) k_debug_gemm_tn(int M, int N, const flo
 }  // namespace
 
 extern "C" {
+
+int psdf_sdf_sphere_trace(int N, int L, int T, const float* pos, const float* dirs, const float* lattice, const float* scale_factor,
+                          const float* shift, const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob,
+                          int nr_iters, float sdf_multiplier, float sdf_converged_tresh, const uint8_t* occupancy, int V, float extent,
+                          const float trans[3], float sphere_radius, const float sphere_center[3], float* pos_out, uint8_t* converged,
+                          void* stream) {
+    if (N < 0 || L < 1 || L > kMaxLevels || (L % 4) != 0 || hidden > 64 || hidden % 16 != 0 || out_dim > 64 || nr_iters < 0)
+        return PSDF_ERR_UNSUPPORTED;
+    if (N == 0) return PSDF_OK;
+    FusedParams P;
+    P.N = N; P.L = L; P.T = T;
+    P.cap_mask = ((T & (T - 1)) == 0) ? (unsigned)(T - 1) : 0u;
+    P.points_scaling = points_scaling;
+    P.in_dim = (L + 2) * 2;
+    if (P.in_dim > 64) return PSDF_ERR_UNSUPPORTED;
+    P.g = make_geom(P.in_dim, hidden, out_dim);
+    TraceParams Q;
+    Q.nr_iters = nr_iters; Q.sdf_mult = sdf_multiplier; Q.conv_thresh = sdf_converged_tresh;
+    Q.has_occ = occupancy ? 1 : 0;
+    const float zero3[3] = {0.f, 0.f, 0.f};
+    Q.grid = psdf::make_grid_geom(occupancy ? V : 1, occupancy ? extent : 1.0f, occupancy ? trans : zero3);
+    Q.sph_radius = sphere_radius; Q.sph_cx = sphere_center[0]; Q.sph_cy = sphere_center[1]; Q.sph_cz = sphere_center[2];
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + kTile * 4 * sizeof(float) + 64;
+    static bool attr_done = false;
+    if (!attr_done) { cudaFuncSetAttribute(k_sdf_sphere_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_done = true; }
+    const int ntiles = div_up(N, kTile);
+    k_sdf_sphere_trace<<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, Q, pos, dirs, reinterpret_cast<const float2*>(lattice), scale_factor,
+                                                                     shift, window, blob, occupancy, pos_out, converged);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
 
 int psdf_debug_umma_gemm_tn(int M, int N, const float* A, const float* B, float* dump, void* stream) {
     if (M < 1 || M > 64 || N < 1 || N > 64) return PSDF_ERR_ARG;

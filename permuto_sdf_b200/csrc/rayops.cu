@@ -387,30 +387,10 @@ k_occ_advance_to_next_occupied(int n, GridGeom g, const float* __restrict__ dirs
                                const uint8_t* __restrict__ occ, uint8_t* __restrict__ within) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
-    const int nv = g.V * g.V * g.V;
-    const float eps = 1e-6f;
-    RayIn r = load_ray(pos_io, dirs, idx);
-    const double max_steps = (double)g.V * sqrt(3.0);
-    float t = 0;
-    int steps = 0;
-    bool wb = true;
-    while (wb && (double)steps < max_steps) {
-        float px = __fmaf_rn(r.dx, t, r.ox), py = __fmaf_rn(r.dy, t, r.oy), pz = __fmaf_rn(r.dz, t, r.oz);
-        int v = pos_to_voxel(px, py, pz, g);
-        bool oob = v > (nv - 1) || v < 0;
-        if (oob) {
-            wb = false;
-            pos_io[3 * idx] = px; pos_io[3 * idx + 1] = py; pos_io[3 * idx + 2] = pz;
-            break;
-        }
-        float dn = dda_step(px, py, pz, r.dx, r.dy, r.dz, r.ix, r.iy, r.iz, g.V);
-        t = __fadd_rn(__fadd_rn(t, dn), eps);
-        if (__ldg(occ + v)) {
-            pos_io[3 * idx] = px; pos_io[3 * idx + 1] = py; pos_io[3 * idx + 2] = pz;
-            break;
-        }
-        steps++;
-    }
+    float px = pos_io[3 * idx], py = pos_io[3 * idx + 1], pz = pos_io[3 * idx + 2];
+    // the march lives in common.cuh (shared with the fused sphere tracer); it leaves the position as it was when its step budget runs out
+    const bool wb = occ_advance_to_next_occupied(g, occ, px, py, pz, dirs[3 * idx], dirs[3 * idx + 1], dirs[3 * idx + 2]);
+    pos_io[3 * idx] = px; pos_io[3 * idx + 1] = py; pos_io[3 * idx + 2] = pz;
     within[idx] = wb ? 1 : 0;
 }
 

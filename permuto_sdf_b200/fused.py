@@ -107,6 +107,34 @@ class FusedSDF:
         return sdf, grad, geom
 
 
+def _fused_sdf_sphere_trace(self, points, dirs, iter_nr, nr_iters, sdf_multiplier, sdf_converged_tresh, occupancy_grid=None):
+    """sphere_trace's iteration loop (sdf_utils.py:150-200) in one kernel: -> (traced points [N,3], converged [N] bool).
+    With an occupancy grid every step is followed by advance_sample_to_next_occupied_voxel, otherwise rays stop when they leave
+    the model's bounding sphere."""
+    if self._versions != self._cur_versions():
+        self.repack()
+    m, enc = self.model, self.model.encoding
+    pts, drs = points.detach().contiguous(), dirs.detach().contiguous()
+    N = pts.shape[0]
+    out = torch.empty_like(pts)
+    conv = torch.empty(N, dtype=torch.bool, device=pts.device)
+    window = m.window(iter_nr).view(-1).contiguous()
+    sph = m.boundary_primitive
+    if occupancy_grid is not None:
+        V, e, t = occupancy_grid._geom()
+        occ = occupancy_grid.m_grid_occupancy
+    else:
+        V, e, t, occ = 1, 1.0, [0.0, 0.0, 0.0], None
+    with torch.no_grad():
+        call("psdf_sdf_sphere_trace", N, enc.nr_levels, enc.capacity, pts, drs, enc.lattice_values.detach(), enc.scale_factor, enc.shift_tensor(),
+             window, enc.concat_points_scaling, self.hidden, self.out_dim, self.blob, int(nr_iters), float(sdf_multiplier),
+             float(sdf_converged_tresh), occ, V, e, t, float(sph.m_radius), sph.m_center, out, conv)
+    return out, conv
+
+
+FusedSDF.sphere_trace = _fused_sdf_sphere_trace
+
+
 def _pad16(v):
     return (v + 15) // 16 * 16
 

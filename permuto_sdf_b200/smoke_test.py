@@ -62,7 +62,7 @@ def run(verbose=True):
     hp = HyperParams()
     hp.max_nr_samples_per_ray = 16
     hp.nr_samples_imp_sampling = 4
-    tr = Trainer(hp, nr_levels=4, capacity=2 ** 12, sdf_hidden=32, occupancy_resolution=64, with_colorcal=False)
+    tr = Trainer(hp, nr_levels=4, capacity=2 ** 12, sdf_hidden=32, occupancy_resolution=64, with_colorcal=False, optimizer="fused")
     tr.set_analytic_scene()
     gt = torch.rand(256, 3, device="cuda"); gm = torch.ones(256, 1, device="cuda")
     loss = tr.step(to, td, gt, gm, None)

@@ -66,6 +66,11 @@ def create_samples(with_mask, hyperparams, ray_origins, ray_dirs, jitter_samples
     return fg, bg
 
 
+# sphere_trace's loop as one tcgen05 kernel instead of ~12 launches + a sync per iteration. Measured on B200 (tools/bench_sphere_trace.py,
+# profiles/README.md): 3x faster than the masked loop at 256x256 rays (4.2 vs 13.2 ms), 2.8x slower at 1920x1080 (67 vs 24 ms) where
+# the loop's per-iteration compaction and its massively parallel occupancy marches win; crossover ~150 k rays.
+FUSED_SPHERE_TRACE = True
+FUSED_SPHERE_TRACE_MAX_RAYS = 131072
 FUSED_IMPORTANCE_ROUND = True     # one launch per round (csrc/volrender.cu k_importance_round) instead of 9
 
 
@@ -189,7 +194,12 @@ def sphere_trace(nr_sphere_traces, ray_origins, ray_dirs, model, return_gradient
         pos, dirs = rsp.samples_pos, rsp.samples_dirs
     pts = pos.clone()
     converged = torch.zeros_like(pos)[:, 0:1].bool()
-    for _ in range(nr_sphere_traces):
+    fused_tracer = FUSED_SPHERE_TRACE and getattr(model, "fused", None) is not None and 0 < pos.shape[0] <= FUSED_SPHERE_TRACE_MAX_RAYS
+    if fused_tracer:
+        # the whole loop below in one kernel (csrc/fused_sdf.cu k_sdf_sphere_trace): same per-ray arithmetic, no gather / scatter / sync
+        pts, _ = model.fused.sphere_trace(pos, dirs, model.last_iter_nr, nr_sphere_traces, sdf_multiplier, sdf_converged_tresh,
+                                          occupancy_grid if has_occupancy else None)
+    for _ in range(0 if fused_tracer else nr_sphere_traces):
         sel = torch.logical_not(converged).view(-1)
         pos_u, dirs_u = pts[sel].contiguous(), dirs[sel].contiguous()
         if pos_u.shape[0] == 0:

@@ -179,3 +179,29 @@ def test_fused_render_loss_equals_modular_iteration(trainer, it, tol_grad):
     assert abs(res[True][0] - res[False][0]) / abs(res[False][0]) < (1e-4 if tol_grad <= 1e-3 else 1e-3)
     assert rel(res[True][2], res[False][2]) < tol_grad
     assert rel(res[True][3], res[False][3]) < 1e-3
+
+
+@pytest.mark.parametrize("with_grid", [True, False])
+def test_fused_sphere_trace_equals_masked_loop(trainer, with_grid):
+    """the single-kernel sphere tracer against the reference-style masked gather / scatter loop on the same network: identical
+    traced points (bit for bit), on a freshly initialised SDF (sphere of radius ~0.3 from geometric init is not needed: any field works)"""
+    import permuto_sdf_b200.train as tr
+    o, d = scenes.make_rays(3000, seed=21, miss_fraction=0.2, axis_aligned=0)
+    to, td = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    m = trainer.model_sdf
+    m.last_iter_nr = 20000
+    with torch.no_grad():       # an SDF-like field: bias the output so that rays do converge somewhere inside the sphere
+        lin = [l for l in m.mlp_sdf if isinstance(l, torch.nn.Linear)]
+        lin[-1].bias[0] = 0.05
+    grid = trainer.occupancy_grid if with_grid else None
+    res = {}
+    for fused in (False, True):
+        tr.FUSED_SPHERE_TRACE = fused
+        with torch.no_grad():           # rendering context: the loop's network evaluations take the same fused tcgen05 path
+            pts, sdf, grads, geom, rsp = tr.sphere_trace(12, to, td, m, True, 0.9, 1e-3, grid)
+        res[fused] = (pts.clone(), sdf.clone(), grads.clone())
+    tr.FUSED_SPHERE_TRACE = True
+    assert res[True][0].shape == res[False][0].shape and res[True][0].shape[0] > 500
+    assert torch.equal(res[True][0], res[False][0]), float((res[True][0] - res[False][0]).abs().max())
+    assert torch.equal(res[True][1], res[False][1])
+    assert torch.equal(rsp.samples_pos, res[True][0])
