@@ -136,6 +136,8 @@ def call(name, *args):
             conv.append(int(a))
     if _STATS is not None:
         _STATS["calls"][name] = _STATS["calls"].get(name, 0) + 1
+        if name in _KERNELS_FN:
+            _STATS["extra"] = _STATS.get("extra", 0) + _KERNELS_FN[name](args) - 1
         if _STATS["events"] is not None:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
@@ -153,7 +155,19 @@ def call(name, *args):
 
 # ---- instrumentation used by bench.py: count C-ABI calls / kernel launches and time them with CUDA events on the
 # launching stream. Kernel launches per entry point (the rest launch exactly one kernel):
-_KERNELS_PER_CALL = {"psdf_packed_compact_scan": 2, "psdf_vr_combine_uniform_samples_with_imp": 3, "psdf_sdf_fused_backward": 2, "psdf_rgb_fused_backward": 2}
+_KERNELS_PER_CALL = {"psdf_packed_compact_scan": 2, "psdf_vr_combine_uniform_samples_with_imp": 3}
+
+
+def _bwd_kernels(args):
+    """fused backward calls launch (reverse sweep, dW) once per chunk of one wave of 128-sample tiles (csrc/fused_*_bwd.cu)"""
+    import torch
+    tiles = (int(args[0]) + 127) // 128
+    chunk = int(os.environ.get("PSDF_BWD_CHUNK_TILES", "0"))
+    chunk = tiles if chunk <= 0 else chunk
+    return 2 * max(1, (tiles + chunk - 1) // chunk)
+
+
+_KERNELS_FN = {"psdf_sdf_fused_backward": _bwd_kernels, "psdf_rgb_fused_backward": _bwd_kernels}
 _STATS = None
 
 
@@ -166,7 +180,7 @@ def stats_end():
     """-> (calls per entry point, kernel launches, {name: (n, total_ms)} if events were recorded)"""
     global _STATS
     st, _STATS = _STATS, None
-    launches = sum(n * _KERNELS_PER_CALL.get(k, 1) for k, n in st["calls"].items())
+    launches = sum(n * _KERNELS_PER_CALL.get(k, 1) for k, n in st["calls"].items()) + st.get("extra", 0)
     times = {}
     if st["events"] is not None:
         import torch

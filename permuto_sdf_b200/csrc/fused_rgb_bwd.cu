@@ -337,8 +337,22 @@ __global__ void __launch_bounds__(128, 1) k_rgb_dw(MlpGeom g, int ntiles, RgbSpi
 
 extern "C" {
 
+// chunked like the SDF backward (fused_sdf_bwd.cu): one wave of tiles per chunk so that the dW kernel reads the spill from L2
+static int rgb_bwd_chunk_tiles(int ntiles) {
+    static int chunk = -1;
+    if (chunk < 0) {
+        const char* e = getenv("PSDF_BWD_CHUNK_TILES");
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        chunk = e ? atoi(e) : 0;      // default: one chunk (measured on B200: per-wave chunks cost more in drain / refill than L2 hits give back)
+        (void)sms;
+    }
+    return (chunk <= 0 || chunk > ntiles) ? ntiles : chunk;
+}
 long long psdf_rgb_fused_backward_workspace_bytes(int N) {
-    return (long long)2 * kNL * div_up(N > 0 ? N : 1, kTile) * kRgbSpillBytes;
+    const int ntiles = div_up(N > 0 ? N : 1, kTile);
+    return (long long)2 * kNL * rgb_bwd_chunk_tiles(ntiles) * kRgbSpillBytes;
 }
 
 int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
@@ -354,9 +368,10 @@ int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* 
     RgbSpill sp;
     float* b[kNL] = {gb0, gb1, gb2, gb3};
     const int ntiles = div_up(N, kTile);
+    const int chunk = rgb_bwd_chunk_tiles(ntiles);
     for (int l = 0; l < kNL; l++) {
-        sp.zt[l] = workspace + (size_t)(2 * l) * ntiles * kRgbSpillBytes;
-        sp.at[l] = workspace + (size_t)(2 * l + 1) * ntiles * kRgbSpillBytes;
+        sp.zt[l] = workspace + (size_t)(2 * l) * chunk * kRgbSpillBytes;
+        sp.at[l] = workspace + (size_t)(2 * l + 1) * chunk * kRgbSpillBytes;
         sp.gbias[l] = b[l];
     }
     int dev = 0, sms = 148;
@@ -369,13 +384,20 @@ int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* 
         cudaFuncSetAttribute(k_rgb_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_done = true;
     }
-    k_rgb_fused_backward<<<min(ntiles, sms), kRgbThreads, smem, ST>>>(P, pos, dirs, sdf_grad, geom, reinterpret_cast<const float2*>(lattice),
-                                                                      scale_factor, shift, window, blob, g_out, grad_lattice, g_sdf_grad,
-                                                                      g_geom, sp);
-    PSDF_CHECK_LAUNCH();
     const size_t smem_dw = (size_t)kDwStages * kDwStageBytes + 128;
-    k_rgb_dw<<<min(ntiles, sms), 128, smem_dw, ST>>>(P.g, ntiles, sp, gW0, gW1, gW2, gW3);
-    PSDF_CHECK_LAUNCH();
+    for (int t0 = 0; t0 < ntiles; t0 += chunk) {
+        const int nt = min(chunk, ntiles - t0);
+        const size_t r0 = (size_t)t0 * kTile;
+        RgbParams Pc = P;
+        Pc.N = (int)min((size_t)nt * kTile, (size_t)N - r0);
+        k_rgb_fused_backward<<<min(nt, sms), kRgbThreads, smem, ST>>>(Pc, pos + r0 * 3, dirs + r0 * 3, sdf_grad + r0 * 3, geom + r0 * kGeomDim,
+                                                                      reinterpret_cast<const float2*>(lattice), scale_factor, shift, window,
+                                                                      blob, g_out + r0 * 3, grad_lattice, g_sdf_grad ? g_sdf_grad + r0 * 3 : nullptr,
+                                                                      g_geom ? g_geom + r0 * kGeomDim : nullptr, sp);
+        PSDF_CHECK_LAUNCH();
+        k_rgb_dw<<<min(nt, sms), 128, smem_dw, ST>>>(P.g, nt, sp, gW0, gW1, gW2, gW3);
+        PSDF_CHECK_LAUNCH();
+    }
     return PSDF_OK;
 }
 

@@ -452,9 +452,27 @@ __global__ void __launch_bounds__(128, 1) k_sdf_dw(MlpGeom g, int ntiles, Spill 
 
 extern "C" {
 
-// workspace: 8 tile spills (zbar_l, a_{l-1} for l = 0..3), each ceil(N/128) x 64 KB, written and consumed inside this call
+// The two kernels can run chunk by chunk (PSDF_BWD_CHUNK_TILES tiles per chunk, same spill buffer every time) so that a chunk's
+// spill is consumed by the dW kernel while it is still in the 126 MB L2. Measured on B200 at N = 65 536: chunks of one wave (148
+// tiles) make the iteration 24 % SLOWER (2.45 vs 1.98 ms) -- the kernels drain and refill the GPU at every chunk boundary and the
+// persistent CTAs lose their amortisation -- so the default is one chunk; keeping the spill in L2 needs the dW product inside the
+// backward kernel itself (round 2).
+static int bwd_chunk_tiles(int ntiles) {
+    static int chunk = -1;
+    if (chunk < 0) {
+        const char* e = getenv("PSDF_BWD_CHUNK_TILES");
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        chunk = e ? atoi(e) : 0;      // default: one chunk (measured on B200: per-wave chunks cost more in drain / refill than L2 hits give back)
+        (void)sms;
+    }
+    return (chunk <= 0 || chunk > ntiles) ? ntiles : chunk;
+}
+// workspace: 8 tile spills (zbar_l, a_{l-1} for l = 0..3) of one chunk, 64 KB per tile each, written and consumed inside this call
 long long psdf_sdf_fused_backward_workspace_bytes(int N) {
-    return (long long)2 * kNL * div_up(N > 0 ? N : 1, kTile) * kSpillTileBytes;
+    const int ntiles = div_up(N > 0 ? N : 1, kTile);
+    return (long long)2 * kNL * bwd_chunk_tiles(ntiles) * kSpillTileBytes;
 }
 
 // grad_lattice, grad_W_l [N_l, K_l] and grad_bias_l are accumulated (+=).
@@ -474,9 +492,10 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
     Spill sp;
     float* b[kNL] = {gb0, gb1, gb2, gb3};
     const int ntiles = div_up(N, kTile);
+    const int chunk = bwd_chunk_tiles(ntiles);
     for (int l = 0; l < kNL; l++) {
-        sp.zt[l] = workspace + (size_t)(2 * l) * ntiles * kSpillTileBytes;
-        sp.at[l] = workspace + (size_t)(2 * l + 1) * ntiles * kSpillTileBytes;
+        sp.zt[l] = workspace + (size_t)(2 * l) * chunk * kSpillTileBytes;
+        sp.at[l] = workspace + (size_t)(2 * l + 1) * chunk * kSpillTileBytes;
         sp.gbias[l] = b[l];
     }
     int dev = 0, sms = 148;
@@ -487,14 +506,23 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
     if ((size_t)128 * (2 * P.g.Kp[0] + 1) * 4 > (size_t)8 * kATileBytes) return PSDF_ERR_UNSUPPORTED;
     static bool attr_done = false;
     if (!attr_done) { cudaFuncSetAttribute(k_sdf_fused_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_done = true; }
-    k_sdf_fused_backward<<<min(ntiles, sms), kBwdThreads, smem, ST>>>(P, pos, reinterpret_cast<const float2*>(lattice), scale_factor, shift,
-                                                                      window, blob, g_sdf, g_grad, g_geom, grad_lattice, sp);
-    PSDF_CHECK_LAUNCH();
     const size_t smem_dw = (size_t)kDwStages * kDwStageBytes + 128;
     static bool attr_dw = false;
     if (!attr_dw) { cudaFuncSetAttribute(k_sdf_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_dw = true; }
-    k_sdf_dw<<<min(ntiles, sms), 128, smem_dw, ST>>>(P.g, ntiles, sp, gW0, gW1, gW2, gW3);
-    PSDF_CHECK_LAUNCH();
+    const int geom_cols = out_dim - 1;
+    for (int t0 = 0; t0 < ntiles; t0 += chunk) {
+        const int nt = min(chunk, ntiles - t0);
+        const size_t r0 = (size_t)t0 * kTile;
+        FusedParams Pc = P;
+        Pc.N = (int)min((size_t)nt * kTile, (size_t)N - r0);
+        k_sdf_fused_backward<<<min(nt, sms), kBwdThreads, smem, ST>>>(Pc, pos + r0 * 3, reinterpret_cast<const float2*>(lattice), scale_factor,
+                                                                      shift, window, blob, g_sdf ? g_sdf + r0 : nullptr,
+                                                                      g_grad ? g_grad + r0 * 3 : nullptr,
+                                                                      g_geom ? g_geom + r0 * geom_cols : nullptr, grad_lattice, sp);
+        PSDF_CHECK_LAUNCH();
+        k_sdf_dw<<<min(nt, sms), 128, smem_dw, ST>>>(P.g, nt, sp, gW0, gW1, gW2, gW3);
+        PSDF_CHECK_LAUNCH();
+    }
     return PSDF_OK;
 }
 

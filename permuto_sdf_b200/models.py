@@ -207,6 +207,10 @@ class SDF(torch.nn.Module):
         if getattr(self, "fused", None) is not None and not torch.is_grad_enabled():
             sdf, _, geom = self.fused(points, iter_nr, with_gradient=False, with_geom=self.geom_feat_size_out != 0)
             return sdf, geom
+        if getattr(self, "fused_training", False) and not points.requires_grad:
+            # parameter gradients wanted, position gradient not: the fused training pair (its extra tangent streams are unused)
+            sdf, _, geom = self.fused.train_forward(points, iter_nr)
+            return sdf, (geom if self.geom_feat_size_out != 0 else None)
         feat = self.encoding(points, self.window(iter_nr).view(-1))
         y = self.mlp_sdf(feat)
         if self.geom_feat_size_out != 0:

@@ -65,11 +65,14 @@ def run(verbose=True):
     tr = Trainer(hp, nr_levels=4, capacity=2 ** 12, sdf_hidden=32, occupancy_resolution=64, with_colorcal=False, optimizer="fused")
     tr.set_analytic_scene()
     gt = torch.rand(256, 3, device="cuda"); gm = torch.ones(256, 1, device="cuda")
-    loss = tr.step(to, td, gt, gm, None)
+    before = tr.model_sdf.encoding.lattice_values.detach().clone()
+    loss = tr.step(to, td, gt, gm, None, optimizer_step=False)
     lv = float(loss)
     assert np.isfinite(lv), "training step produced a non finite loss"
     gnorm = float(tr.model_sdf.encoding.lattice_values.grad.abs().sum())
     assert gnorm > 0, "no gradient reached the SDF lattice"
+    tr.optimizer_step()                      # fused AdamW over the flat buffers (zeroes the gradients in the same pass)
+    assert not torch.equal(before, tr.model_sdf.encoding.lattice_values.detach()), "the optimizer did not move the SDF lattice"
     if verbose:
         print("smoke ok: enc rel err %.2e, pos-grad rel err %.2e, %d samples, loss %.4f" % (e1, e2, tr.last["nr_samples"], lv))
     return True
