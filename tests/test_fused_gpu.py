@@ -155,7 +155,7 @@ def test_umma_transposed_gemm_weight_gradient_layout(cuda, M, N):
     assert lanes == list(range(M)) or lanes == [(m // 16) * 32 + (m % 16) for m in range(M)], lanes
 
 
-@pytest.mark.parametrize("L,N,it", [(16, 5000, 20000), (8, 129, 0), (16, 65536, 20000)])
+@pytest.mark.parametrize("L,N,it", [(16, 5000, 20000), (8, 129, 0), (24, 2000, 20000), (16, 65536, 20000)])
 def test_fused_rgb_forward_matches_model(cuda, L, N, it):
     """fused colour network (encoding + SH + normal + geom -> Lipschitz MLP on tcgen05) against the modular RGB model"""
     from permuto_sdf import Sphere
@@ -183,7 +183,7 @@ def test_fused_rgb_forward_matches_model(cuda, L, N, it):
     assert float((x - want_lin).abs().max() / want_lin.abs().max()) < 1e-3
 
 
-@pytest.mark.parametrize("L,N,it", [(16, 3000, 20000), (8, 129, 0), (16, 40000, 20000)])
+@pytest.mark.parametrize("L,N,it", [(16, 3000, 20000), (8, 129, 0), (24, 1000, 20000), (16, 40000, 20000)])
 def test_fused_rgb_training_gradients_match_autograd(cuda, L, N, it):
     """fused colour-network backward (reverse sweep + tensor-core dW + lattice scatter + normal / geom gradients) against autograd
     through the modular RGB model"""

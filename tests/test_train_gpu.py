@@ -205,3 +205,29 @@ def test_fused_sphere_trace_equals_masked_loop(trainer, with_grid):
     assert torch.equal(res[True][0], res[False][0]), float((res[True][0] - res[False][0]).abs().max())
     assert torch.equal(res[True][1], res[False][1])
     assert torch.equal(rsp.samples_pos, res[True][0])
+
+
+def test_reference_default_sizes_iteration(cuda):
+    """the reference's own network sizes (24 levels, 32-wide SDF MLP: models.py:131-160, 309-340) go through the fused kernels too"""
+    from permuto_sdf import PermutoSDF
+    from permuto_sdf_b200.train import HyperParams, Trainer
+    hp = HyperParams()
+    hp.max_nr_samples_per_ray = 32
+    hp.nr_samples_imp_sampling = 8
+    hp.min_dist_between_samples = 1e-3
+    tr = Trainer(hp, nr_levels=24, capacity=2 ** 15, sdf_hidden=32, occupancy_resolution=64, nr_images=4, seed=2, optimizer="fused")
+    tr.set_analytic_scene()
+    assert tr.model_sdf.fused is not None and tr.model_sdf.fused_training and tr.model_rgb.fused is not None
+
+    class Reel:
+        pass
+    rgb, mask, K, tf = scenes.synthetic_reel(nimg=4, H=60, W=80)
+    reel = Reel()
+    reel.rgb_reel, reel.mask_reel, reel.K_reel, reel.tf_world_cam_reel = [torch.from_numpy(a).cuda() for a in (rgb, mask, K, tf)]
+    before = [p.detach().clone() for p in tr.params]
+    for i in range(2):
+        o, d, gt, gm, img = PermutoSDF.random_rays_from_reel(reel, 256)
+        loss = float(tr.step(o, d, gt, gm, img))
+        assert np.isfinite(loss)
+    moved = [float((a - b.detach()).abs().max()) for a, b in zip(before, tr.params)]
+    assert max(moved) > 0 and all(np.isfinite(m) for m in moved)

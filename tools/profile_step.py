@@ -49,6 +49,14 @@ def main():
     print(ka.table(sort_by="self_cpu_time_total", row_limit=45, max_name_column_width=70))
     nk = sum(e.count for e in ka if e.device_type == torch.autograd.DeviceType.CUDA)
     print("device kernels+memops per step:", nk / n)
+    print("=== device kernels by launch count (per step), with mean duration")
+    rows = [(e.count / n, e.device_time_total / max(e.count, 1), e.key) for e in ka if e.device_type == torch.autograd.DeviceType.CUDA]
+    for c, t, k in sorted(rows, reverse=True)[:60]:
+        print("%7.1f  %8.2f us  %s" % (c, t, k[:110]))
+    print("=== torch ops by call count (per step)")
+    rows = [(e.count / n, e.key) for e in ka if e.device_type != torch.autograd.DeviceType.CUDA and e.count >= n]
+    for c, k in sorted(rows, reverse=True)[:50]:
+        print("%7.1f  %s" % (c, k[:100]))
 
 
 if __name__ == "__main__":
