@@ -192,7 +192,7 @@ __device__ __forceinline__ float gelu_d2(float z) {   // d/dz [Phi(z) + z phi(z)
 // issue the three split products of one [128 x Kp] x [Np x Kp]^T GEMM into TMEM (single thread).
 // Descriptor convention validated on B200 by tests/test_fused_gpu.py::test_umma_gemm_self_test: the first offset field
 // (LBO) is the stride between core matrices adjacent along K, the second (SBO) between 8-row groups.
-__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
+__device__ __forceinline__ void issue_gemm_rebuild(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
                                            const uint8_t* w_lo, int Kp, int Np) {
     const uint32_t idesc = umma::make_idesc(128, Np, umma::kFmtBF16);
     const uint32_t sbo_w = (Kp / 8) * kLBO;
@@ -207,6 +207,22 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a_hi,
     }
 }
 
+
+// same products with the four descriptors built once and only their start-address field advanced per K step (fewer
+// instructions on the single issuing thread); this is the variant the kernels use, issue_gemm_rebuild stays as its cross-check
+__device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
+                                                   const uint8_t* w_lo, int Kp, int Np) {
+    const uint32_t idesc = umma::make_idesc(128, Np, umma::kFmtBF16);
+    const uint32_t sbo_w = (Kp / 8) * kLBO;
+    const uint64_t dah0 = umma::make_desc(umma::smem_u32(a_hi), kLBO, kSBO_A), dal0 = umma::make_desc(umma::smem_u32(a_lo), kLBO, kSBO_A);
+    const uint64_t dwh0 = umma::make_desc(umma::smem_u32(w_hi), kLBO, sbo_w), dwl0 = umma::make_desc(umma::smem_u32(w_lo), kLBO, sbo_w);
+    for (int kk = 0; kk < Kp / 16; kk++) {
+        const uint64_t off = (uint64_t)(kk * ((2 * kLBO) >> 4));
+        umma::mma_bf16(tmem_d, dah0 + off, dwh0 + off, idesc, kk > 0 ? 1u : 0u);
+        umma::mma_bf16(tmem_d, dah0 + off, dwl0 + off, idesc, 1u);
+        umma::mma_bf16(tmem_d, dal0 + off, dwh0 + off, idesc, 1u);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------- backward helpers
 constexpr unsigned kFull = 0xffffffffu;

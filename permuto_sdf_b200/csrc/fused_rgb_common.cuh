@@ -74,14 +74,13 @@ __device__ __forceinline__ void issue_gemm_w(uint32_t tmem_d, const uint8_t* a_h
                                              int Kp, int Np) {
     const uint32_t idesc = umma::make_idesc(128, Np, umma::kFmtBF16);
     const uint32_t sbo_w = (Kp / 8) * kLBO;
-    const uint32_t ah = umma::smem_u32(a_hi), al = umma::smem_u32(a_lo), wh = umma::smem_u32(w_hi), wl = umma::smem_u32(w_lo);
+    const uint64_t dah0 = umma::make_desc(umma::smem_u32(a_hi), kLBO, kWSBO), dal0 = umma::make_desc(umma::smem_u32(a_lo), kLBO, kWSBO);
+    const uint64_t dwh0 = umma::make_desc(umma::smem_u32(w_hi), kLBO, sbo_w), dwl0 = umma::make_desc(umma::smem_u32(w_lo), kLBO, sbo_w);
     for (int kk = 0; kk < Kp / 16; kk++) {
-        const uint32_t ko = kk * 2 * kLBO;
-        const uint64_t dah = umma::make_desc(ah + ko, kLBO, kWSBO), dal = umma::make_desc(al + ko, kLBO, kWSBO);
-        const uint64_t dwh = umma::make_desc(wh + ko, kLBO, sbo_w), dwl = umma::make_desc(wl + ko, kLBO, sbo_w);
-        umma::mma_bf16(tmem_d, dah, dwh, idesc, kk > 0 ? 1u : 0u);
-        umma::mma_bf16(tmem_d, dah, dwl, idesc, 1u);
-        umma::mma_bf16(tmem_d, dal, dwh, idesc, 1u);
+        const uint64_t off = (uint64_t)(kk * ((2 * kLBO) >> 4));      // start-address field, 16-byte units
+        umma::mma_bf16(tmem_d, dah0 + off, dwh0 + off, idesc, kk > 0 ? 1u : 0u);
+        umma::mma_bf16(tmem_d, dah0 + off, dwl0 + off, idesc, 1u);
+        umma::mma_bf16(tmem_d, dal0 + off, dwh0 + off, idesc, 1u);
     }
 }
 

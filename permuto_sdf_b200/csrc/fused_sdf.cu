@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(kTile) k_debug_gemm(int N, int K, const float*
     umma::fence_after_sync();
     const uint32_t tmem_base = *slot;
     if (tid == 0) {
-        issue_gemm(tmem_base, a_hi, a_lo, w_hi, w_lo, Kp, Np);
+        if (K == 63) issue_gemm_rebuild(tmem_base, a_hi, a_lo, w_hi, w_lo, Kp, Np);     // K = 63 selects the rebuild-per-step variant
+        else issue_gemm(tmem_base, a_hi, a_lo, w_hi, w_lo, Kp, Np);
         umma::commit(bar);
     }
     umma::mbar_wait(bar, 0);

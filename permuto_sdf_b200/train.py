@@ -57,12 +57,12 @@ def create_samples(with_mask, hyperparams, ray_origins, ray_dirs, jitter_samples
     else:
         fg = RaySampler.compute_samples_fg(ray_origins, ray_dirs, ray_t_entry, ray_t_exit, hyperparams.min_dist_between_samples,
                                            hyperparams.max_nr_samples_per_ray, bounding_primitive.m_radius,
-                                           bounding_primitive.m_center_tensor, jitter_samples)
+                                           bounding_primitive.m_center, jitter_samples)
     fg = fg.compact_to_valid_samples()
     bg = None
     if not with_mask:
         bg = RaySampler.compute_samples_bg(ray_origins, ray_dirs, ray_t_exit, hyperparams.nr_samples_bg, bounding_primitive.m_radius,
-                                           bounding_primitive.m_center_tensor, jitter_samples, False)
+                                           bounding_primitive.m_center, jitter_samples, False)
     return fg, bg
 
 

@@ -44,3 +44,23 @@ def test_device_iter_comparisons_narrow_range():
     with pytest.raises(TypeError):
         d == 100
     assert int(d) == 100 and math.isclose(float(d), 100.0)
+
+
+def test_splitk_weight_gradient_matches_plain_gemm():
+    """host logic of the split-K weight-gradient product (fused.splitk_tn / SplitKLinearFn) on CPU tensors"""
+    from permuto_sdf_b200.fused import SplitKLinearFn, splitk_tn
+    torch.manual_seed(0)
+    for rows in (10, 2048, 4100):
+        a, b = torch.randn(rows, 7, dtype=torch.float64), torch.randn(rows, 5, dtype=torch.float64)
+        assert torch.allclose(splitk_tn(a, b), a.t() @ b, rtol=1e-12, atol=1e-12)
+    x = torch.randn(4100, 6, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(3, 6, dtype=torch.float64, requires_grad=True)
+    bias = torch.randn(3, dtype=torch.float64, requires_grad=True)
+    y = SplitKLinearFn.apply(x, w, bias)
+    y.pow(2).sum().backward()
+    g = [t.grad.clone() for t in (x, w, bias)]
+    for t in (x, w, bias):
+        t.grad = None
+    torch.nn.functional.linear(x, w, bias).pow(2).sum().backward()
+    for a, t in zip(g, (x, w, bias)):
+        assert torch.allclose(a, t.grad, rtol=1e-10, atol=1e-10)

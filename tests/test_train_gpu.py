@@ -231,3 +231,42 @@ def test_reference_default_sizes_iteration(cuda):
         assert np.isfinite(loss)
     moved = [float((a - b.detach()).abs().max()) for a, b in zip(before, tr.params)]
     assert max(moved) > 0 and all(np.isfinite(m) for m in moved)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_iteration_with_background_model(cuda, graph):
+    """--no mask path (train_permuto_sdf.py:155-171): NeRF++ background model composited behind the SDF foreground; the fused NeuS
+    kernel blends bg_transmittance * bg_rgb and hands its gradient back to the background network; also under CUDA-graph replay"""
+    from permuto_sdf import PermutoSDF
+    from permuto_sdf_b200.train import HyperParams, Trainer
+    hp = HyperParams()
+    hp.with_mask = False
+    hp.max_nr_samples_per_ray = 24
+    hp.nr_samples_imp_sampling = 8
+    hp.nr_samples_bg = 16
+    hp.min_dist_between_samples = 1e-3
+    tr = Trainer(hp, nr_levels=8, capacity=2 ** 14, sdf_hidden=32, occupancy_resolution=64, nr_images=4, seed=5, optimizer="fused")
+    tr.set_analytic_scene()
+    assert tr.model_bg is not None
+    if graph:
+        tr.enable_cuda_graph(warmup_steps=1)
+
+    class Reel:
+        pass
+    rgb, mask, K, tf = scenes.synthetic_reel(nimg=4, H=60, W=80)
+    reel = Reel()
+    reel.rgb_reel, reel.mask_reel, reel.K_reel, reel.tf_world_cam_reel = [torch.from_numpy(a).cuda() for a in (rgb, mask, K, tf)]
+    bg0 = tr.model_bg.encoding.lattice_values.detach().clone()
+    gen = torch.Generator().manual_seed(3)
+    losses = []
+    for i in range(4):
+        pix = torch.randint(0, 60 * 80, (256,), generator=gen, dtype=torch.int32).cuda()
+        img = torch.randint(0, 4, (256,), generator=gen, dtype=torch.int32).cuda()
+        with torch.no_grad():
+            o, d, gt, gm, idx = PermutoSDF.rays_from_reel_indices(reel, pix, img)
+        losses.append(float(tr.step(o, d, gt, gm, idx)))
+    tr.disable_cuda_graph()
+    from permuto_sdf import OccupancyGrid, RaySampler, RaySamplesPacked, VolumeRendering
+    RaySamplesPacked.static_capacity = False
+    assert all(np.isfinite(l) for l in losses), losses
+    assert not torch.equal(bg0, tr.model_bg.encoding.lattice_values.detach()), "the background model received no gradient"
