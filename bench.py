@@ -174,8 +174,11 @@ def run_ours(args):
         loss = tr.step(o, d, gt, gm, img_idx, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1))
         if world > 1:
             # the single collective of the path: one NCCL all-reduce of the flat gradient buffer, mean folded into AdamW
-            dist.all_reduce(tr.optimizer.flat_grad if flat is None else flat.flat, op=dist.ReduceOp.SUM)
-            tr.optimizer_step(grad_scale=1.0 / world)
+            if flat is None and os.environ.get("PSDF_NCCL_IN_GRAPH", "0") == "1":
+                tr.optimizer_step(grad_scale=1.0 / world, allreduce=True)       # captured in the optimizer graph
+            else:
+                dist.all_reduce(tr.optimizer.flat_grad if flat is None else flat.flat, op=dist.ReduceOp.SUM)
+                tr.optimizer_step(grad_scale=1.0 / world)
         if e2e:
             return float(loss)          # device -> host read of the step's result
         return loss

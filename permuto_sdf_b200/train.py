@@ -468,30 +468,38 @@ class Trainer:
         _, launches, _ = stats_end()
         return dict(graph=g, static=static, loss=out, last=self.last, shapes=shapes, lo=dit.lo, hi=dit.hi, launches=launches)
 
-    def _optimizer_step_graphed(self, grad_scale):
+    def _optimizer_step_graphed(self, grad_scale, allreduce=False):
+        """allreduce=True: the data-parallel sum of the flat gradient buffer (NCCL) is part of the step -- captured in the optimizer
+        graph, so that a replayed iteration is two graph launches and nothing else"""
         cg = self._cg
+        if allreduce:
+            import torch.distributed as dist
         if cg["fb"] is None:            # still in the eager warm-up iterations
             side, cur = cg["stream"], torch.cuda.current_stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
+                if allreduce:
+                    dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
                 self.optimizer.step(grad_scale=grad_scale)
                 self.model_sdf.fused.repack()
                 cg["it_dev"].add_(1.0)
             cur.wait_stream(side)
         else:
-            og = cg["opt"].get(grad_scale)
+            og = cg["opt"].get((grad_scale, allreduce))
             if og is None:
                 from ._lib import stats_begin, stats_end
                 torch.cuda.synchronize()
                 stats_begin(with_events=False)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=cg["stream"]):
+                    if allreduce:
+                        dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
                     self.optimizer.step(grad_scale=grad_scale)
                     self.model_sdf.fused.repack()
                     cg["it_dev"].add_(1.0)
                 _, launches, _ = stats_end()
                 self.optimizer.step_count -= 1          # capture records, it does not run
-                og = cg["opt"][grad_scale] = dict(graph=g, launches=launches)
+                og = cg["opt"][(grad_scale, allreduce)] = dict(graph=g, launches=launches)
             og["graph"].replay()
             self.optimizer.step_count += 1
         if cg["it_host"] is not None:
@@ -504,9 +512,12 @@ class Trainer:
             return None
         return cg["fb"]["launches"] + sum(o["launches"] for o in cg["opt"].values())
 
-    def optimizer_step(self, grad_scale=1.0):
+    def optimizer_step(self, grad_scale=1.0, allreduce=False):
         if self._cg is not None:
-            return self._optimizer_step_graphed(float(grad_scale))
+            return self._optimizer_step_graphed(float(grad_scale), bool(allreduce))
+        if allreduce:
+            import torch.distributed as dist
+            dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
         if hasattr(self.optimizer, "flat_grad"):
             self.optimizer.step(grad_scale=grad_scale)
             if getattr(self.model_sdf, "fused", None) is not None:
