@@ -221,6 +221,7 @@ def run_ours(args):
     ms_dev, launches, ktimes, clocks, avg_samples = timed(e2e=False, with_events=not graphed)
     ms_e2e, _, _, clocks2, _ = timed(e2e=True, with_events=False)
     ms_per_step = ms_dev / args.steps
+    prof_steps = 0
     if graphed:
         # kernels inside the replayed graphs (counted at capture) + the eager calls of the timed region (occupancy refresh)
         launches += tr.graph_launches_per_step() * args.steps
@@ -238,14 +239,17 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel of OUR library inside the timed region (CUDA events on the launch stream)
     hbm, peak_src = peaks()
-    L, C, Ns = 16, 36, avg_samples
-    alg_bytes = {   # algorithmic bytes per launch, SURVEY.md 8(d)
-        "psdf_enc_forward": lambda: Ns * (12 + L * 4 * 8 + C * 4),
-        "psdf_enc_backward": lambda: Ns * (12 + L * 8 + L * 4 * 8 + L * 4 * 8),
-        "psdf_enc_double_backward": lambda: Ns * (12 + 12 + L * 8 + L * 4 * 8 + L * 4 * 8 + C * 4),
-        "psdf_sdf_fused_forward": lambda: Ns * (12 + L * 4 * 8 + 4 + 12 + 128),
-        "psdf_sdf_fused_backward": lambda: Ns * (12 + 2 * L * 4 * 8 + 4 + 12 + 128),
+    L, C = 16, 36
+    alg_bytes = {   # algorithmic bytes per SAMPLE; multiplied by the samples the timed launches actually processed
+        "psdf_enc_forward": 12 + L * 4 * 8 + C * 4,
+        "psdf_enc_backward": 12 + L * 8 + L * 4 * 8 + L * 4 * 8,
+        "psdf_enc_double_backward": 12 + 12 + L * 8 + L * 4 * 8 + L * 4 * 8 + C * 4,
+        "psdf_sdf_fused_forward": 12 + L * 4 * 8 + 4 + 12 + 128,
+        "psdf_sdf_fused_backward": 12 + 2 * L * 4 * 8 + 4 + 12 + 128,
+        "psdf_rgb_fused_forward": 12 + L * 4 * 8 + 12 + 12 + 128 + 12,
+        "psdf_rgb_fused_backward": 12 + 2 * L * 4 * 8 + 12 + 12 + 128 + 12 + 12 + 128,
     }
+    units = dict(_lib.LAST_UNITS)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
     # (profiles/r1_ncu_fused_kernels.csv; value + tangent variant of the forward kernel)
     ncu_traffic = {"psdf_sdf_fused_forward": 17.59e6 + 0.23e6, "psdf_sdf_fused_backward": 73.6e6 + 244.4e6}
@@ -255,9 +259,12 @@ def run_ours(args):
         name = next((k for _, k in top if k in alg_bytes), top[0][1])
         n, tot_ms = ktimes[name]
         per_launch_s = tot_ms / n / 1e3
-        ach = (alg_bytes[name]() / per_launch_s / 1e9) if name in alg_bytes else None
+        # samples processed by the timed launches of this entry point (the profiling pass is rescaled to the timed step count)
+        nsamp = units.get(name, 0) * (args.steps / prof_steps if prof_steps else 1.0)
+        ach = (alg_bytes[name] * nsamp / (tot_ms / 1e3) / 1e9) if name in alg_bytes and nsamp else None
         roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": (ach / hbm) if ach else None,
-                "traffic": ncu_traffic.get(name), "launches": n, "avg_us": per_launch_s * 1e6, "peak_source": peak_src,
+                "traffic": ncu_traffic.get(name), "launches": n, "avg_us": per_launch_s * 1e6, "samples_per_launch": nsamp / n if n else None,
+                "peak_source": peak_src,
                 "share_of_step": tot_ms / ms_dev,
                 "top5_ms_per_step": {k: round(v / args.steps, 4) for v, k in top[:5]}}
 

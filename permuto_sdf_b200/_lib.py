@@ -136,6 +136,9 @@ def call(name, *args):
             conv.append(int(a))
     if _STATS is not None:
         _STATS["calls"][name] = _STATS["calls"].get(name, 0) + 1
+        if args and isinstance(args[0], int):            # leading count argument (samples / rays) of the entry point
+            u = _STATS.setdefault("units", {})
+            u[name] = u.get(name, 0) + int(args[0])
         if name in _KERNELS_FN:
             _STATS["extra"] = _STATS.get("extra", 0) + _KERNELS_FN[name](args) - 1
         if _STATS["events"] is not None:
@@ -169,6 +172,7 @@ def _bwd_kernels(args):
 
 _KERNELS_FN = {"psdf_sdf_fused_backward": _bwd_kernels, "psdf_rgb_fused_backward": _bwd_kernels}
 _STATS = None
+LAST_UNITS = {}        # {entry point: sum of its leading count argument} of the last stats window
 
 
 def stats_begin(with_events=False):
@@ -179,7 +183,9 @@ def stats_begin(with_events=False):
 def stats_end():
     """-> (calls per entry point, kernel launches, {name: (n, total_ms)} if events were recorded)"""
     global _STATS
+    global LAST_UNITS
     st, _STATS = _STATS, None
+    LAST_UNITS = st.get("units", {})
     launches = sum(n * _KERNELS_PER_CALL.get(k, 1) for k, n in st["calls"].items()) + st.get("extra", 0)
     times = {}
     if st["events"] is not None:

@@ -237,9 +237,9 @@ class _NeusRenderLossFn(torch.autograd.Function):
         rsp = ctx.rsp
         cos_f, cos_dev, gt_rgb, gt_mask, hit, s_rgb, s_mask, s_eik, n_dev = ctx.cfg
         # rows outside every ray (gaps of slot-strided containers, the zero tail of static-capacity ones) get no gradient
-        g_sdf = torch.zeros_like(sdf)
-        g_grad = torch.zeros_like(grad)
-        g_rgb = torch.zeros_like(rgb)
+        flat = torch.zeros(sdf.shape[0] * 7, device=sdf.device)            # one zero-fill for the three gradients
+        n1 = sdf.shape[0]
+        g_sdf, g_grad, g_rgb = flat[:n1].view_as(sdf), flat[n1:4 * n1].view_as(grad), flat[4 * n1:].view_as(rgb)
         g_bg = torch.empty_like(bg) if ctx.has_bg and ctx.needs_input_grad[5] else None
         g_inv = torch.zeros(1, device=sdf.device) if ctx.needs_input_grad[4] else None
         call("psdf_neus_render_loss_backward", *rsp._rsp(), sdf, grad, rgb, rsp.samples_dirs, rsp.samples_dt, inv_s, cos_f, cos_dev, gt_rgb,
@@ -388,7 +388,10 @@ class _FusedRGBTrainFn(torch.autograd.Function):
         dims = [fr.in_dim] + fr.h + [3]
         in_place = getattr(enc, "grad_in_place", False) and lattice.grad is not None and lattice.grad.is_contiguous() and \
             all(l.bias.grad is not None and l.bias.grad.is_contiguous() for l in fr.layers)
-        gW = [torch.zeros(dims[l + 1], dims[l], device=dev) for l in range(4)]      # wrt the normalised weights: flows on through autograd
+        sizes = [dims[l + 1] * dims[l] for l in range(4)]                           # wrt the normalised weights: flows on through autograd
+        offs = [0, sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]]
+        flat_w = torch.zeros(sum(sizes), device=dev)                                # one zero-fill for the four matrices
+        gW = [flat_w[offs[l]:offs[l] + sizes[l]].view(dims[l + 1], dims[l]) for l in range(4)]
         gb = [l.bias.grad for l in fr.layers] if in_place else [torch.zeros(dims[l + 1], device=dev) for l in range(4)]
         g_sg = torch.empty_like(sg)          # every row is written by the kernel
         g_gm = torch.empty_like(gm)

@@ -87,13 +87,14 @@ class RaySamplesPacked:
     CUDA graph. The default (False) sizes the compacted container exactly, with the reference's host sync."""
     static_capacity = False
 
-    def __init__(self, nr_rays, nr_samples_maximum, zero=False):
+    def __init__(self, nr_rays, nr_samples_maximum, zero=False, zero_count=True):
         d = _dev()
         self.m_nr_rays = int(nr_rays)
         self.max_nr_samples = int(nr_samples_maximum)
         M = self.max_nr_samples
         self.is_compact = False
-        self.cur_nr_samples = torch.zeros(1, dtype=torch.int32, device=d)
+        # the samplers add into the counter (it must start at zero); compaction / merge / resampling overwrite or ignore it
+        self.cur_nr_samples = torch.zeros(1, dtype=torch.int32, device=d) if zero_count else torch.empty(1, dtype=torch.int32, device=d)
         if zero:
             # one zero-filled arena (a single memset) carved into the per-sample arrays; offsets keep 16-byte alignment
             Mp = (M + 3) // 4 * 4
@@ -158,7 +159,7 @@ class RaySamplesPacked:
             exact = self.max_nr_samples if static else int(ws[R + nblocks].item())
         else:
             exact = 0
-        out = RaySamplesPacked(R, exact, zero=static)
+        out = RaySamplesPacked(R, exact, zero=static, zero_count=False)
         out.is_compact = True
         out.has_sdf = self.has_sdf
         out.rays_have_equal_nr_of_samples = self.rays_have_equal_nr_of_samples
@@ -518,7 +519,7 @@ class VolumeRendering:
     def importance_sample(ray_origins, ray_dirs, rsp, sample_cdf, nr_importance_samples, jitter_samples):
         R = rsp.ray_start_end_idx.shape[0]
         k = int(nr_importance_samples)
-        imp = RaySamplesPacked(R, R * k)
+        imp = RaySamplesPacked(R, R * k, zero_count=False)
         imp.rays_have_equal_nr_of_samples = True
         imp.fixed_nr_of_samples_per_ray = k
         call("psdf_vr_importance_sample", *rsp._rsp(), _f32(ray_origins, "ray_origins", 3), _f32(ray_dirs, "ray_dirs", 3),
@@ -534,7 +535,7 @@ class VolumeRendering:
         (one round of importance_sampling_sdf_model); bit-identical to the separate calls, same generator use"""
         R = rsp.ray_start_end_idx.shape[0]
         k = int(nr_importance_samples)
-        imp = RaySamplesPacked(R, R * k)
+        imp = RaySamplesPacked(R, R * k, zero_count=False)
         imp.rays_have_equal_nr_of_samples = True
         imp.fixed_nr_of_samples_per_ray = k
         cdf = torch.zeros(VolumeRendering._N(rsp), 1, device=rsp.samples_z.device)
@@ -555,7 +556,7 @@ class VolumeRendering:
         R = rsp.ray_start_end_idx.shape[0]
         k = rsp_imp.fixed_nr_of_samples_per_ray
         c_max = VolumeRendering._N(rsp) + R * k
-        comb = RaySamplesPacked(R, max(c_max, 1), zero=RaySamplesPacked.static_capacity)
+        comb = RaySamplesPacked(R, max(c_max, 1), zero=RaySamplesPacked.static_capacity, zero_count=False)
         comb.is_compact = True          # the merge writes ray after ray at the scanned offsets
         if RaySamplesPacked.static_capacity and rsp.has_sdf:
             comb._samples_sdf = comb._zero_sdf

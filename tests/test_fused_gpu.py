@@ -225,3 +225,54 @@ def test_fused_rgb_training_gradients_match_autograd(cuda, L, N, it):
         assert rel(a["W"][l], b["W"][l]) < 1e-3, ("W", l, rel(a["W"][l], b["W"][l]))
         assert rel(a["b"][l], b["b"][l]) < 1e-3, ("b", l, rel(a["b"][l], b["b"][l]))
         assert float((a["c"][l] - b["c"][l]).abs().max()) < 1e-3 * max(1e-6, float(b["c"][l].abs().max())) + 1e-7, ("c", l)
+
+
+@pytest.mark.parametrize("N", [1, 127, 128, 130])
+def test_fused_kernels_tile_boundaries(cuda, N):
+    """sample counts around the 128-row tile size (and a single sample) through every fused kernel pair: values and parameter
+    gradients agree with the modular autograd path"""
+    from permuto_sdf import Sphere
+    from permuto_sdf_b200.models import RGB, SDF
+    torch.manual_seed(N)
+    sph = Sphere(0.5, [0, 0, 0])
+    pts = (torch.rand(N, 3, device="cuda") - 0.5) * 0.8
+    rel = lambda x, y: float((x - y).abs().max() / (y.abs().max() + 1e-20))
+    # ---- SDF
+    m = SDF(3, sph, 32, 10000, nr_levels=8, capacity=2 ** 12, hidden=32).to("cuda")
+    with torch.no_grad():
+        m.encoding.lattice_values.normal_(0, 0.3)
+    res = {}
+    for fused in (False, True):
+        if fused:
+            m.enable_fused_training()
+        m.zero_grad()
+        sdf, grad, geom = m.get_sdf_and_gradient(pts.clone(), 20000)
+        ((grad.norm(dim=-1) - 1) ** 2).sum().add(sdf.sum()).add(geom.pow(2).sum()).backward()
+        lin = [l for l in m.mlp_sdf if isinstance(l, torch.nn.Linear)]
+        res[fused] = (sdf.detach(), grad.detach(), m.encoding.lattice_values.grad.clone(), [l.weight.grad.clone() for l in lin])
+    assert rel(res[True][0], res[False][0]) < 1e-3 and rel(res[True][1], res[False][1]) < 1e-3
+    assert rel(res[True][2], res[False][2]) < 1e-3
+    for a, b in zip(res[True][3], res[False][3]):
+        assert rel(a, b) < 1e-3
+    # ---- colour network
+    c = RGB(3, sph, 32, 1, nr_levels=8, capacity=2 ** 12).to("cuda")
+    with torch.no_grad():
+        c.encoding.lattice_values.normal_(0, 0.3)
+    c.fused_head = False
+    dirs = torch.nn.functional.normalize(torch.randn(N, 3, device="cuda"), dim=-1)
+    g0, f0 = torch.randn(N, 3, device="cuda"), torch.randn(N, 32, device="cuda")
+    res = {}
+    for fused in (False, True):
+        if fused:
+            c.enable_fused()
+        c.zero_grad()
+        g, f = g0.clone().requires_grad_(True), f0.clone().requires_grad_(True)
+        out = c(pts, dirs, g, f, 20000)
+        out.pow(2).sum().backward()
+        res[fused] = (out.detach(), g.grad.clone(), f.grad.clone(), c.encoding.lattice_values.grad.clone(),
+                      [l.weight.grad.clone() for l in c.mlp.layers])
+    assert float((res[True][0] - res[False][0]).abs().max()) < 1e-4
+    for i in (1, 2, 3):
+        assert rel(res[True][i], res[False][i]) < 1e-3, i
+    for a, b in zip(res[True][4], res[False][4]):
+        assert rel(a, b) < 1e-3
