@@ -136,6 +136,26 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
                 umma::bulk_wait_read0();
                 umma::commit(&bars[1]);
             }
+            // while the MMAs run: gelu'(z^(l-1)) of this thread's column chunks from the TMEM-resident pre-activations
+            const int Kp = P.g.Kp[l];
+            float g1a[16], g1b[16];                       // chunks grp and grp + 4 (Kp <= 128 -> at most two chunks per thread)
+            if (l > 0) {
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int c = grp + j * kRgbGroups;
+                    if (c < Kp / 16) {
+                        float z[16];
+                        umma::tmem_ld16(tmem_z[l - 1] + lane_off + c * 16, z);
+                        umma::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) {
+                            const float zz = z[i] + s_bias[(l - 1) * 128 + c * 16 + i];
+                            const GeluEval ge = gelu_eval(zz);
+                            (j == 0 ? g1a : g1b)[i] = fmaf(zz, ge.pdf, ge.cdf);
+                        }
+                    }
+                }
+            }
             umma::mbar_wait(&bars[1], mma_phase);
             mma_phase ^= 1;
             umma::fence_after_sync();
@@ -143,19 +163,16 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
                 if (l > 0) load_layer_weights(s_w, blob, P.g, l - 1, true, &bars[0]);
                 else if (tile + (int)gridDim.x < ntiles) load_layer_weights(s_w, blob, P.g, 0, false, &bars[0]);
             }
-            const int Kp = P.g.Kp[l];
             if (l > 0) {
-                for (int c = grp; c < Kp / 16; c += kRgbGroups) {
-                    float ab[16], z[16];
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int c = grp + j * kRgbGroups;
+                    if (c >= Kp / 16) continue;
+                    float ab[16];
                     umma::tmem_ld16(tmem_work + lane_off + c * 16, ab);
-                    umma::tmem_ld16(tmem_z[l - 1] + lane_off + c * 16, z);
                     umma::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float zz = z[i] + s_bias[(l - 1) * 128 + c * 16 + i];
-                        const GeluEval ge = gelu_eval(zz);
-                        ab[i] *= fmaf(zz, ge.pdf, ge.cdf);
-                    }
+                    for (int i = 0; i < 16; i++) ab[i] *= (j == 0 ? g1a : g1b)[i];
                     store8w(s_z, s_z + kWTileBytes, row, 2 * c, ab);
                     store8w(s_z, s_z + kWTileBytes, row, 2 * c + 1, ab + 8);
                     if (!valid) {

@@ -255,6 +255,24 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                 umma::bulk_wait_read0();
                 umma::commit(&bars[1]);
             }
+            // while the MMAs run: the GELU' / GELU'' factors of layer l-1 depend only on pre-activations that are already in TMEM
+            const int cr = grp;
+            const bool have_chunk = cr < P.g.Kp[l] / 16;
+            float g1[16], g2t[16];
+            if (l > 0 && have_chunk) {
+                float z[16], tz[16];
+                const uint32_t tst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2 * (l - 1) * 64;
+                umma::tmem_ld16(tst + cr * 16, z);
+                umma::tmem_ld16(tst + 64 + cr * 16, tz);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float zz = z[i] + s_bias[(l - 1) * 64 + cr * 16 + i];
+                    const GeluEval ge = gelu_eval(zz);
+                    g1[i] = fmaf(zz, ge.pdf, ge.cdf);
+                    g2t[i] = ge.pdf * (2.0f - zz * zz) * tz[i];
+                }
+            }
             umma::mbar_wait(&bars[1], mma_phase);
             umma::fence_after_sync();
             {
@@ -266,18 +284,11 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                     umma::tmem_ld16(twork + c * 16, ab);
                     umma::tmem_ld16(twork + 64 + c * 16, tab_);
                     if (l > 0) {
-                        float z[16], tz[16];
-                        const uint32_t tst = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + 2 * (l - 1) * 64;
-                        umma::tmem_ld16(tst + c * 16, z);
-                        umma::tmem_ld16(tst + 64 + c * 16, tz);
                         umma::tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; i++) {
-                            float zz = z[i] + s_bias[(l - 1) * 64 + c * 16 + i];
-                            const GeluEval ge = gelu_eval(zz);
-                            const float g1 = fmaf(zz, ge.pdf, ge.cdf), g2 = ge.pdf * (2.0f - zz * zz);
-                            float zb = g1 * ab[i] + g2 * tz[i] * tab_[i];
-                            tab_[i] = g1 * tab_[i];
+                            const float zb = g1[i] * ab[i] + g2t[i] * tab_[i];
+                            tab_[i] = g1[i] * tab_[i];
                             ab[i] = zb;
                         }
                         // ab = zbar_{l-1}, tab_ = tzbar_{l-1}
