@@ -74,15 +74,16 @@ def test_graph_replay_reproduces_eager_iterations(cuda):
 
 
 def test_graph_training_trajectory(cuda):
-    """with the real learning rate the two trajectories stay together (losses per iteration, sample counts); Adam steps every
-    touched parameter by ~lr whatever the gradient's size, so entries whose gradient is round-off noise can go either way and
-    the parameters are compared through the losses they produce, not entry by entry"""
+    """with the real learning rate the two trajectories stay together (losses per iteration, sample counts). This is a statistical
+    statement: the float atomics of the scatter kernels make even two EAGER runs differ in the last bits, and Adam (eps = 1e-15)
+    steps every touched parameter by ~lr whatever the gradient's size, so entries whose gradient is round-off noise go either way
+    and the difference grows over the iterations -- hence percent-level tolerances here; the exact comparison is the lr = 0 test above"""
     l_e, n_e, p_e, _, _ = _run("eager")
     l_g, n_g, p_g, _, _ = _run("graph")
     assert all(np.isfinite(l_g))
     for a, b in zip(l_e, l_g):
-        assert abs(a - b) / abs(a) < 5e-3, (l_e, l_g)
-    assert max(abs(a - b) for a, b in zip(n_e, n_g)) <= 0.02 * max(n_e)
+        assert abs(a - b) / abs(a) < 5e-2, (l_e, l_g)
+    assert max(abs(a - b) for a, b in zip(n_e, n_g)) <= 0.05 * max(n_e)
     p_0 = _run("eager", steps=0)[2]
     moved = sum(float(((a - b) ** 2).sum()) for a, b in zip(p_g, p_0)) ** 0.5
     assert moved > 1e-2, "the replayed optimizer graph must move the parameters"
