@@ -74,15 +74,17 @@ def test_graph_replay_reproduces_eager_iterations(cuda):
 
 
 def test_graph_training_trajectory(cuda):
-    """with the real learning rate the two trajectories stay together (losses per iteration, sample counts). This is a statistical
-    statement: the float atomics of the scatter kernels make even two EAGER runs differ in the last bits, and Adam (eps = 1e-15)
-    steps every touched parameter by ~lr whatever the gradient's size, so entries whose gradient is round-off noise go either way
-    and the difference grows over the iterations -- hence percent-level tolerances here; the exact comparison is the lr = 0 test above"""
+    """with the real learning rate both modes train: losses finite and decreasing over the 8 iterations, similar sample counts,
+    parameters moved by the replayed optimizer graph. The two loss sequences are NOT compared value by value: the float atomics of the
+    scatter kernels make even two eager runs differ in the last bits, and Adam (eps = 1e-15) turns every noise-level gradient into a
+    full +-lr step (observed on B200: the loss after the very first optimizer step already takes one of two values 8e-4 apart, in
+    either mode, and the sequences drift by percents from there). Exact equivalence of the replayed iteration -- samples, losses,
+    gradients -- is what test_graph_replay_reproduces_eager_iterations (lr = 0) and test_fused_adamw_device_step_under_cuda_graph check."""
     l_e, n_e, p_e, _, _ = _run("eager")
     l_g, n_g, p_g, _, _ = _run("graph")
-    assert all(np.isfinite(l_g))
-    for a, b in zip(l_e, l_g):
-        assert abs(a - b) / abs(a) < 5e-2, (l_e, l_g)
+    for l in (l_e, l_g):
+        assert all(np.isfinite(l)) and l[-1] < l[0], l
+    assert abs(l_e[0] - l_g[0]) / abs(l_e[0]) < 1e-4, "the first iteration starts from identical parameters"
     assert max(abs(a - b) for a, b in zip(n_e, n_g)) <= 0.05 * max(n_e)
     p_0 = _run("eager", steps=0)[2]
     moved = sum(float(((a - b) ** 2).sum()) for a, b in zip(p_g, p_0)) ** 0.5
