@@ -164,14 +164,9 @@ def run_ours(args):
     img_dev = [p.to(dev) for p in img_host]
 
     def one_step(i, e2e):
-        if e2e:
-            pix = pix_host[i].to(dev, non_blocking=True)
-            img = img_host[i].to(dev, non_blocking=True)
-        else:
-            pix, img = pix_dev[i], img_dev[i]
-        with torch.no_grad():
-            o, d, gt, gm, img_idx = PermutoSDF.rays_from_reel_indices(reel, pix, img)
-        loss = tr.step(o, d, gt, gm, img_idx, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1))
+        # e2e: the step's inputs start in pinned host memory; otherwise they are device resident
+        pix, img = (pix_host[i], img_host[i]) if e2e else (pix_dev[i], img_dev[i])
+        loss = tr.step_from_reel(reel, pix, img, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1))
         if world > 1:
             # the single collective of the path: one NCCL all-reduce of the flat gradient buffer, mean folded into AdamW
             if flat is None and os.environ.get("PSDF_NCCL_IN_GRAPH", "0") == "1":

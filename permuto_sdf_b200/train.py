@@ -411,12 +411,26 @@ class Trainer:
             cg["it_dev"].fill_(float(self.iter_nr))
             cg["it_host"] = self.iter_nr
 
-    def _step_graphed(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy, optimizer_step):
+    def step_from_reel(self, tensor_reel, pixel_indices, image_indices, update_occupancy=None, optimizer_step=True):
+        """one iteration from (pixel, image) indices into a TensorReel: ray generation (PermutoSDF.rays_from_reel_indices) + step.
+        Under CUDA-graph replay the indices are the graph's inputs -- host (pinned) or device int32 tensors, copied straight into the
+        static buffers -- and the ray-generation kernel is part of the replayed graph."""
+        make_rays = lambda pix, img: PermutoSDF.rays_from_reel_indices(tensor_reel, pix, img)
+        if self._cg is None:
+            dev = self.optimizer.flat_param.device if hasattr(self.optimizer, "flat_param") else torch.device("cuda", torch.cuda.current_device())
+            with torch.no_grad():
+                o, d, gt, gm, idx = make_rays(pixel_indices.to(dev, non_blocking=True), image_indices.to(dev, non_blocking=True))
+            return self.step(o, d, gt, gm, idx, update_occupancy=update_occupancy, optimizer_step=optimizer_step)
+        self.model_sdf.train(); self.model_rgb.train()
+        return self._step_graphed(pixel_indices, image_indices, None, None, None, update_occupancy, optimizer_step, make_rays=make_rays)
+
+    def _step_graphed(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy, optimizer_step, make_rays=None):
         cg = self._cg
         it = self.iter_nr
         self._sync_device_iter()
-        inputs = [ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices]
-        shapes = tuple(None if t is None else (tuple(t.shape), t.dtype) for t in inputs)
+        # with make_rays the graph inputs are (pixel indices, image indices) and ray generation is captured with the iteration
+        inputs = [ray_origins, ray_dirs] if make_rays is not None else [ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices]
+        shapes = (make_rays is not None,) + tuple(None if t is None else (tuple(t.shape), t.dtype) for t in inputs)
         fb = cg["fb"]
         valid = fb is not None and fb["shapes"] == shapes and fb["lo"] <= it < fb["hi"]
         cur = torch.cuda.current_stream()
@@ -426,14 +440,18 @@ class Trainer:
             side = cg["stream"]
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                loss = self.losses(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, DeviceIter(it, cg["it_dev"]))
+                args = inputs
+                if make_rays is not None:
+                    with torch.no_grad():
+                        args = make_rays(*[t.to(cg["it_dev"].device, non_blocking=True) for t in inputs])
+                loss = self.losses(*args, DeviceIter(it, cg["it_dev"]))
                 self.optimizer.zero_grad(set_to_none=False)
                 loss.backward()
                 loss = loss.detach()
             cur.wait_stream(side)
         else:
             if not valid:
-                fb = cg["fb"] = self._capture_forward_backward(inputs, shapes, it)
+                fb = cg["fb"] = self._capture_forward_backward(inputs, shapes, it, make_rays)
             for dst, src in zip(fb["static"], inputs):
                 if dst is not None:
                     dst.copy_(src, non_blocking=True)
@@ -452,9 +470,9 @@ class Trainer:
         self.iter_nr += 1
         return loss
 
-    def _capture_forward_backward(self, inputs, shapes, it):
+    def _capture_forward_backward(self, inputs, shapes, it, make_rays=None):
         cg = self._cg
-        static = [None if t is None else t.detach().clone() for t in inputs]
+        static = [None if t is None else t.detach().to(cg["it_dev"].device).clone() for t in inputs]
         dit = DeviceIter(it, cg["it_dev"])
         self.optimizer.zero_grad(set_to_none=False)
         torch.cuda.synchronize()
@@ -462,7 +480,11 @@ class Trainer:
         stats_begin(with_events=False)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=cg["stream"]):
-            loss = self.losses(*static, dit)
+            args = static
+            if make_rays is not None:
+                with torch.no_grad():
+                    args = make_rays(*static)
+            loss = self.losses(*args, dit)
             loss.backward()
             out = loss.detach()
         _, launches, _ = stats_end()

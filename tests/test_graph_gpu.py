@@ -46,10 +46,13 @@ def _run(mode, steps=8, start_iter=60000, lr=None, grad_at_last=False):
     for i in range(steps):
         pix = torch.randint(0, 60 * 80, (256,), generator=gen, dtype=torch.int32).cuda()
         img = torch.randint(0, 4, (256,), generator=gen, dtype=torch.int32).cuda()
-        with torch.no_grad():
-            o, d, gt, gm, idx = PermutoSDF.rays_from_reel_indices(reel, pix, img)
         last = grad_at_last and i == steps - 1
-        losses.append(float(tr.step(o, d, gt, gm, idx, optimizer_step=not last)))
+        if mode == "graph":         # indices in, ray generation captured with the iteration
+            losses.append(float(tr.step_from_reel(reel, pix, img, optimizer_step=not last)))
+        else:
+            with torch.no_grad():
+                o, d, gt, gm, idx = PermutoSDF.rays_from_reel_indices(reel, pix, img)
+            losses.append(float(tr.step(o, d, gt, gm, idx, optimizer_step=not last)))
         counts.append(int(tr.last["nr_samples_dev"]))
     params = [p.detach().clone() for p in tr.params]
     grad = tr.optimizer.flat_grad.detach().clone()
