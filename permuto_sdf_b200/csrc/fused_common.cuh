@@ -226,6 +226,11 @@ __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const uint8_t* a_hi,
 
 // ---------------------------------------------------------------------------------------------- backward helpers
 constexpr unsigned kFull = 0xffffffffu;
+// Warp aggregation of the lattice scatter (match_any + segmented shuffle sum, one red per distinct vertex) pays where the 32
+// neighbouring samples of a warp share vertices: on levels whose cells are larger than the sample spacing. On the fine levels
+// (scale factor 1 / (sqrt(2) sigma) above this bound, i.e. sigma below ~3.5e-3) hardly any two lanes meet, so they issue their reds
+// directly and skip the match.
+constexpr float kAggregateBelowScale = 200.0f;
 __device__ __forceinline__ float2 add_peers2(unsigned peers, float2 x, int lane) {
     int rel = __popc(peers << (31 - lane) << 1);
     peers &= (0xfffffffeu << lane);

@@ -210,15 +210,20 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
                 const float w = lc->window[l];
                 const float a0 = xr[2 * l], a1 = xr[2 * l + 1];
                 float* gtab = grad_lattice + (size_t)l * P.T * 2;
+                const bool aggregate = lc->scale[l * 4] < kAggregateBelowScale;       // warp-uniform (l is)
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     const unsigned idx = vindex3(s, r, P.cap_mask, (unsigned)P.T);
                     const float cb = s.bary[r] * w;
                     float2 cv = make_float2(cb * a0, cb * a1);
-                    const unsigned key = valid ? idx : 0xffffffffu;
-                    const unsigned peers = __match_any_sync(kFull, key);
-                    cv = add_peers2(peers, cv, lane);
-                    if (valid && lane == __ffs(peers) - 1) red_v2(gtab + (size_t)idx * 2, cv);
+                    if (aggregate) {
+                        const unsigned key = valid ? idx : 0xffffffffu;
+                        const unsigned peers = __match_any_sync(kFull, key);
+                        cv = add_peers2(peers, cv, lane);
+                        if (valid && lane == __ffs(peers) - 1) red_v2(gtab + (size_t)idx * 2, cv);
+                    } else if (valid) {
+                        red_v2(gtab + (size_t)idx * 2, cv);
+                    }
                 }
             }
             if (valid) {

@@ -340,15 +340,20 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                 const float w = lc->window[l];
                 const float a0 = xr[2 * l], a1 = xr[2 * l + 1], t0 = xr[K0 + 2 * l], t1 = xr[K0 + 2 * l + 1];
                 float* gtab = grad_lattice + (size_t)l * P.T * 2;
+                const bool aggregate = lc->scale[l * 4] < kAggregateBelowScale;       // warp-uniform (l is)
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     unsigned idx = vindex3(s, r, P.cap_mask, (unsigned)P.T);
                     float cb = s.bary[r] * w, cd = db[r] * w;
                     float2 cv = make_float2(cb * a0 + cd * t0, cb * a1 + cd * t1);
-                    unsigned key = valid ? idx : 0xffffffffu;
-                    unsigned peers = __match_any_sync(kFull, key);
-                    cv = add_peers2(peers, cv, lane);
-                    if (valid && lane == __ffs(peers) - 1) red_v2(gtab + (size_t)idx * 2, cv);
+                    if (aggregate) {
+                        unsigned key = valid ? idx : 0xffffffffu;
+                        unsigned peers = __match_any_sync(kFull, key);
+                        cv = add_peers2(peers, cv, lane);
+                        if (valid && lane == __ffs(peers) - 1) red_v2(gtab + (size_t)idx * 2, cv);
+                    } else if (valid) {
+                        red_v2(gtab + (size_t)idx * 2, cv);
+                    }
                 }
             }
         }
