@@ -160,8 +160,6 @@ __device__ __forceinline__ GeluEval gelu_eval(float z) {
     o.pdf = 0.3989422804014327f * E;
     return o;
 }
-__device__ __forceinline__ float gelu_f(float z) { return z * gelu_eval(z).cdf; }
-__device__ __forceinline__ float gelu_d(float z) { GeluEval g = gelu_eval(z); return fmaf(z, g.pdf, g.cdf); }
 
 struct FusedParams {
     int N, L, T;
@@ -185,9 +183,6 @@ __device__ __forceinline__ void store8(uint8_t* a_hi, uint8_t* a_lo, int row, in
     *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-__device__ __forceinline__ float gelu_d2(float z) {   // d/dz [Phi(z) + z phi(z)] = phi(z) (2 - z^2)
-    return 0.3989422804014327f * __expf(-0.5f * z * z) * (2.0f - z * z);
-}
 
 // issue the three split products of one [128 x Kp] x [Np x Kp]^T GEMM into TMEM (single thread).
 // Descriptor convention validated on B200 by tests/test_fused_gpu.py::test_umma_gemm_self_test: the first offset field

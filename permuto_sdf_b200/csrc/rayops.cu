@@ -3,11 +3,11 @@
 // Compiled with -fmad=false: every FMA below is explicit and placed where the reference's nvcc build
 // contracts (see common.cuh). Reference semantics cited per kernel.
 //
-// Work mapping (B200): DDA marchers are one thread per ray because the voxel walk is a serial
-// float recurrence (t += step + eps) that must be reproduced bit-for-bit; the occupancy bytes they need
-// do not feed the recurrence, so they are fetched in batches of kBatch independent loads (L2-resident
-// 16.8 MB grid) instead of one dependent load per step. Copy/packing kernels are warp-per-ray with
-// coalesced accesses. Slots in the sample pool are deterministic (ray * stride) rather than handed out
+// Work mapping (B200): the voxel walk is a serial float recurrence (t += step + eps) that must be reproduced
+// bit-for-bit, but the occupancy bytes do not feed it. The sampler used in training runs one WARP per ray with
+// speculative 32-step windows (see k_occ_samples_in_occupied); the first-sample / advance marchers of sphere tracing
+// are one thread per ray with an 8-step look-ahead of the recurrence over the loads (common.cuh). Copy/packing
+// kernels are warp-per-ray with coalesced accesses. Slots in the sample pool are deterministic (ray * stride) rather than handed out
 // by a global atomic, with the reference's atomic order available as slot_mode=0.
 #include "common.cuh"
 #include "sh.cuh"
@@ -19,7 +19,6 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxSteps = 4096;  // OccupancyGridGPU.cuh:24
-constexpr int kBatch = 8;
 
 // ------------------------------------------------------------------------------------------------ Sphere
 // SphereGPU.cuh:21-93. FMA placement copied from the reference SASS: dot(a,b)=fma(az,bz,fma(ax,bx,ay*by)).
