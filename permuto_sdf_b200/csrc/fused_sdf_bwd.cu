@@ -1,6 +1,6 @@
 // Training backward of the fused encoding + SDF MLP (sm_100a, tcgen05): given d loss / d {sdf, d sdf/dx, geom}
-// per sample it produces the lattice gradient (scatter-add fused in the kernel), the bias gradients, and the
-// per-sample layer adjoints / activations whose products are the weight gradients.
+// per sample it produces the lattice gradient (scatter-add fused in the kernel), the bias gradients, and -- through the
+// spilled per-sample layer adjoints / activations -- the weight gradients (second kernel, tensor cores).
 //
 // What it replaces in the reference: `loss.backward()` through SDF.get_sdf_and_gradient
 // (permuto_sdf_py/models/models.py:199-259, create_graph=True) -- i.e. the double backward of the
@@ -20,14 +20,14 @@
 //
 // Kernel structure per 128-sample tile (512 threads: row = tid & 127, group g = tid >> 7 owns operand cores g, g+4, ..
 // in the encoder phases and the 16-column chunk g in the epilogues):
-//   1. encoder (both groups): a_0, ta_0 -> bf16 hi/lo operand tiles in smem, and to the dW spill buffer;
+//   1. encoder (all four groups): a_0, ta_0 -> bf16 hi/lo operand tiles in smem (later spilled as they are, by TMA store);
 //   2. forward recompute, layers 1..3, 2 streams, tcgen05 (weights from one TMA bulk copy); the pre-activations
 //      z_l, tz_l STAY in TMEM (6 x 64 columns) for the reverse sweep; a_l, ta_l go to operand tiles + spill;
 //   3. reverse sweep, layers 4..1: zbar/tzbar tiles -> tcgen05 with the transposed weights (second bulk copy)
 //      -> abar/tabar -> elementwise with gelu', gelu'' from the TMEM-resident z;
 //   4. encoder backward (both groups): warp-aggregated red.global.add.v2.f32 into the lattice gradient.
-// dW itself is formed outside from the spilled [2N, 64] matrices with 4 plain library GEMMs (cuBLAS through
-// torch.matmul); folding them into this kernel (M=64 MMAs on transposed tiles) is the next step.
+// dW is formed by the second kernel of this file (k_sdf_dw) from the operand tiles that phases 1-3 spill by TMA store:
+// the sample axis becomes the MMA K dimension and the tiles are consumed as MN-major operands, exactly as stored.
 #include "fused_common.cuh"
 #include "../../include/psdf_b200.h"
 
