@@ -45,7 +45,8 @@ def _worker(rank, world, port, q):
         loss.backward()
         assert params[0].grad.data_ptr() == flat.flat.data_ptr(), "gradients must accumulate inside the flat buffer"
         dist.all_reduce(flat.flat, op=dist.ReduceOp.SUM)
-        q.put((rank, flat.flat.clone(), lo, hi))
+        # plain Python data through the queue: tensors would travel as shared-memory handles that die with this process
+        q.put((rank, flat.flat.tolist(), lo, hi))
     finally:
         dist.destroy_process_group()
 
@@ -63,6 +64,7 @@ def test_flat_gradient_allreduce_matches_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     res.sort(key=lambda t: t[0])
+    res = [(r, torch.tensor(v), lo, hi) for r, v, lo, hi in res]
     assert torch.equal(res[0][1], res[1][1]), "ranks disagree after the all-reduce"
     assert (res[0][2], res[0][3], res[1][2], res[1][3]) == (0, 5, 5, 10)
     # single-process reference on the whole batch
