@@ -235,13 +235,14 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
 /* Fused sphere tracing (sphere_trace, permuto_sdf_py/utils/sdf_utils.py:120-218): nr_iters iterations of
  *   sdf = SDF(p); p += dir * sdf * sdf_multiplier; converged |= |sdf| < tresh | left the occupied region / bounding sphere
  * with advance_sample_to_next_occupied_voxel applied after every step when an occupancy grid is given (occupancy != NULL; else
- * the bounding-sphere test). One CTA traces 128 rays to the end; pos [N,3] start points, dirs [N,3]; pos_out [N,3], converged [N]
- * (may be NULL). Bit-identical to the masked Python loop on the per-op kernels. */
+ * the bounding-sphere test). Persistent CTAs of 128 ray slots pull rays from a global queue and refill finished slots;
+ * pos [N,3] start points, dirs [N,3]; pos_out [N,3], converged [N] (may be NULL); queue_counter: device int32 [2], ZERO on entry:
+ * [0] scratch (ray queue), [1] += number of network evaluations of the launch (statistics). Bit-identical per ray to the masked Python loop on the per-op kernels. */
 int psdf_sdf_sphere_trace(int N, int L, int T, const float* pos, const float* dirs, const float* lattice, const float* scale_factor,
                           const float* shift, const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob,
                           int nr_iters, float sdf_multiplier, float sdf_converged_tresh, const uint8_t* occupancy, int V, float extent,
                           const float trans[3], float sphere_radius, const float sphere_center[3], float* pos_out, uint8_t* converged,
-                          void* stream);
+                          int* queue_counter, void* stream);
 /* Training backward of psdf_sdf_fused_forward (double backward of encoding + MLP on the tensor cores, two kernels):
  * upstream gradients g_sdf [N], g_grad [N,3], g_geom [N,out_dim-1] (any may be NULL) -> grad_lattice (+=), weight gradients
  * gW_l [N_l, K_l] (+=) and bias gradients gb_l [N_l] (+=). workspace: psdf_sdf_fused_backward_workspace_bytes(N) bytes of
@@ -277,9 +278,12 @@ int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* 
 /* ---------------------------------------------------------------- dense fused AdamW (torch.optim.AdamW / apex FusedAdam math,
  * train_permuto_sdf.py:293-304); step >= 1 is the incremented step count; grad is multiplied by grad_scale and, when
  * zero_grad != 0, reset to zero in the same pass. Pointers 16-byte aligned. step_dev [1] (device int32), when not NULL,
- * replaces `step` so that the call can be replayed from a CUDA graph. */
+ * replaces `step` so that the call can be replayed from a CUDA graph; hyper_dev [2] (device float: lr, weight_decay), when not
+ * NULL, replaces `lr` / `weight_decay` the same way (LR schedulers and the wd = 1.0 switch of train_permuto_sdf.py:400-403 edit
+ * param_groups between replays of one captured graph). */
 int psdf_adamw_step(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, int step, const int* step_dev, float grad_scale, int zero_grad, void* stream);
+                    float eps, float weight_decay, int step, const int* step_dev, const float* hyper_dev, float grad_scale, int zero_grad,
+                    void* stream);
 
 /* self-test of the tensor-core path: D[128,N] = A[128,K] * B[N,K]^T (N,K <= 64) */
 int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream);

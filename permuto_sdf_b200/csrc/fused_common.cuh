@@ -227,6 +227,12 @@ constexpr unsigned kFull = 0xffffffffu;
 // directly and skip the match.
 constexpr float kAggregateBelowScale = 200.0f;
 __device__ __forceinline__ float2 add_peers2(unsigned peers, float2 x, int lane) {
+    // coarse levels: the 32 neighbouring samples of a warp very often all hit the same vertex -> plain butterfly (10 shuffles)
+    if (__all_sync(kFull, peers == kFull)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { x.x += __shfl_xor_sync(kFull, x.x, o); x.y += __shfl_xor_sync(kFull, x.y, o); }
+        return x;
+    }
     int rel = __popc(peers << (31 - lane) << 1);
     peers &= (0xfffffffeu << lane);
     while (__any_sync(kFull, peers)) {

@@ -236,18 +236,25 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
 k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_in, const float* __restrict__ dirs,
                    const float2* __restrict__ lattice, const float* __restrict__ scale, const float* __restrict__ shift,
                    const float* __restrict__ window, const uint8_t* __restrict__ blob, const uint8_t* __restrict__ occ,
-                   float* __restrict__ pos_out, uint8_t* __restrict__ converged_out) {
+                   float* __restrict__ pos_out, uint8_t* __restrict__ converged_out, int* __restrict__ queue) {
+    // Persistent CTAs over a global ray queue: a CTA owns 128 ray SLOTS; a slot whose ray has finished (converged, left the occupied
+    // region, or used its nr_iters evaluations) writes its result and is refilled with the next unclaimed ray (one warp-aggregated
+    // atomicAdd per warp and iteration), so every network evaluation runs on a full tile until the frame is drained. Per ray the
+    // arithmetic is unchanged (results are stored by ray index), so the traced points stay bit-identical to the masked loop.
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_blob = smem;
     uint8_t* s_a = smem + P.g.total;                       // {hi, lo} x 16 KB
     LevelC* lc = reinterpret_cast<LevelC*>(s_a + 2 * kATileBytes);
-    float* s_pos = reinterpret_cast<float*>(lc + 1);       // [128][3]
-    int* s_conv = reinterpret_cast<int*>(s_pos + kTile * 3);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_conv + kTile);
+    float* s_pos = reinterpret_cast<float*>(lc + 1);       // [128][3] current point of the slot's ray
+    float* s_dir = s_pos + kTile * 3;                      // [128][3]
+    int* s_ray = reinterpret_cast<int*>(s_dir + kTile * 3);   // [128] ray index of the slot, -1: empty
+    int* s_it = s_ray + kTile;                             // [128] evaluations done for the slot's ray
+    int* s_flag = s_it + kTile;                            // [0]: queue drained
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_flag + 2);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (kTile - 1), grp = tid >> 7;
-    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); s_flag[0] = 0; }
     for (int i = tid; i < P.L * 3; i += kFusedThreads) {
         lc->scale[(i / 3) * 4 + (i % 3)] = scale[i];
         lc->shift[(i / 3) * 4 + (i % 3)] = shift ? shift[i] : 0.0f;
@@ -259,6 +266,18 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
         umma::mbar_expect_tx(&bars[0], (uint32_t)P.g.total);
         umma::bulk_g2s(s_blob, blob, (uint32_t)P.g.total, &bars[0]);
     }
+    // first assignment: CTA b starts with rays [128 b, 128 b + 128); the queue counter hands out the rays past 128 * gridDim.x
+    if (grp == 0) {
+        const int n = blockIdx.x * kTile + row;
+        const bool ok = n < P.N;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            s_pos[row * 3 + i] = ok ? pos_in[(size_t)n * 3 + i] : 0.0f;
+            s_dir[row * 3 + i] = ok ? dirs[(size_t)n * 3 + i] : 0.0f;
+        }
+        s_ray[row] = ok ? n : -1;
+        s_it[row] = 0;
+    }
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
@@ -267,94 +286,93 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
     uint32_t mma_phase = 0;
     const int level_cores = P.L / 4, all_cores = P.g.Kp[0] / 8;
     const float* bias3 = reinterpret_cast<const float*>(s_blob + P.g.bias[kNL - 1]);
+    const int first_queued = gridDim.x * kTile;
 
-    const int ntiles = (P.N + kTile - 1) / kTile;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int n = tile * kTile + row;
-        const bool valid = n < P.N;
-        if (grp == 0) {
+    int evaluations = 0;                                      // network evaluations of this CTA (same value in every thread)
+    while (true) {
+        const bool active = s_ray[row] >= 0;
+        const int nact = __syncthreads_count(active);
+        if (nact == 0) break;                                // no ray left in this tile (and the queue is drained)
+        evaluations += nact / kGroups;
+        float x[3] = {s_pos[row * 3], s_pos[row * 3 + 1], s_pos[row * 3 + 2]};
+        if (active && Q.nr_iters > 0) {
+            for (int kc = grp; kc < all_cores; kc += kGroups) {
+                float fv[8];
+                if (kc < level_cores) {
 #pragma unroll
-            for (int i = 0; i < 3; i++) s_pos[row * 3 + i] = valid ? pos_in[(size_t)n * 3 + i] : 0.0f;
-            s_conv[row] = valid ? 0 : 1;
-        }
-        __syncthreads();
-        for (int it = 0; it < Q.nr_iters; it++) {
-            const bool active = s_conv[row] == 0;
-            if (__syncthreads_and(!active)) break;           // every ray of the tile has converged
-            float x[3] = {s_pos[row * 3], s_pos[row * 3 + 1], s_pos[row * 3 + 2]};
-            if (active) {
-                for (int kc = grp; kc < all_cores; kc += kGroups) {
-                    float fv[8];
-                    if (kc < level_cores) {
+                    for (int q = 0; q < 4; q++) {
+                        const int l = kc * 4 + q;
+                        float cf[3], e[4];
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            const int l = kc * 4 + q;
-                            float cf[3], e[4];
+                        for (int i = 0; i < 3; i++) cf[i] = __fmul_rn(__fadd_rn(x[i], lc->shift[l * 4 + i]), lc->scale[l * 4 + i]);
+                        elevate3(cf, e);
+                        Simplex3 s;
+                        locate3(e, s);
+                        const float2* tab = lattice + (size_t)l * P.T;
+                        float2 v[4];
 #pragma unroll
-                            for (int i = 0; i < 3; i++) cf[i] = __fmul_rn(__fadd_rn(x[i], lc->shift[l * 4 + i]), lc->scale[l * 4 + i]);
-                            elevate3(cf, e);
-                            Simplex3 s;
-                            locate3(e, s);
-                            const float2* tab = lattice + (size_t)l * P.T;
-                            float2 v[4];
+                        for (int r = 0; r < 4; r++) v[r] = __ldg(tab + vindex3(s, r, P.cap_mask, (unsigned)P.T));
+                        const float w = lc->window[l];
+                        float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-                            for (int r = 0; r < 4; r++) v[r] = __ldg(tab + vindex3(s, r, P.cap_mask, (unsigned)P.T));
-                            const float w = lc->window[l];
-                            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-                            for (int r = 0; r < 4; r++) { float wr = s.bary[r] * w; a0 = fmaf(v[r].x, wr, a0); a1 = fmaf(v[r].y, wr, a1); }
-                            fv[2 * q] = a0; fv[2 * q + 1] = a1;
-                        }
-                    } else {
-                        const int c0 = 2 * P.L;
-#pragma unroll
-                        for (int i = 0; i < 8; i++) {
-                            int c = kc * 8 + i - c0;
-                            float val = 0.f;
-#pragma unroll
-                            for (int d = 0; d < 3; d++) if (c == d && (c0 + c) < P.in_dim) val = x[d] * P.points_scaling;
-                            fv[i] = val;
-                        }
+                        for (int r = 0; r < 4; r++) { float wr = s.bary[r] * w; a0 = fmaf(v[r].x, wr, a0); a1 = fmaf(v[r].y, wr, a1); }
+                        fv[2 * q] = a0; fv[2 * q + 1] = a1;
                     }
-                    store8(s_a, s_a + kATileBytes, row, kc, fv);
+                } else {
+                    const int c0 = 2 * P.L;
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        int c = kc * 8 + i - c0;
+                        float val = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) if (c == d && (c0 + c) < P.in_dim) val = x[d] * P.points_scaling;
+                        fv[i] = val;
+                    }
                 }
+                store8(s_a, s_a + kATileBytes, row, kc, fv);
             }
+        }
 #pragma unroll 1
-            for (int l = 0; l < kNL; l++) {
-                umma::fence_async_smem();
-                umma::fence_before_sync();
-                __syncthreads();
-                if (tid == 0) {
-                    umma::fence_after_sync();
-                    issue_gemm(tmem_base, s_a, s_a + kATileBytes, s_blob + P.g.w_hi[l], s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
-                    umma::commit(&bars[1]);
-                }
-                umma::mbar_wait(&bars[1], mma_phase);
-                mma_phase ^= 1;
+        for (int l = 0; l < kNL; l++) {
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            __syncthreads();
+            if (tid == 0) {
                 umma::fence_after_sync();
-                const float* bias = reinterpret_cast<const float*>(s_blob + P.g.bias[l]);
-                const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-                const int c = grp;
-                if (l < kNL - 1) {
-                    if (c < P.g.Np[l] / 16) {
-                        float z[16];
-                        umma::tmem_ld16(trow + c * 16, z);
-                        umma::tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; i++) { const float zz = z[i] + bias[c * 16 + i]; z[i] = zz * gelu_eval(zz).cdf; }
-                        store8(s_a, s_a + kATileBytes, row, 2 * c, z);
-                        store8(s_a, s_a + kATileBytes, row, 2 * c + 1, z + 8);
-                    }
-                } else if (grp == 0) {
+                issue_gemm(tmem_base, s_a, s_a + kATileBytes, s_blob + P.g.w_hi[l], s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
+                umma::commit(&bars[1]);
+            }
+            umma::mbar_wait(&bars[1], mma_phase);
+            mma_phase ^= 1;
+            umma::fence_after_sync();
+            const float* bias = reinterpret_cast<const float*>(s_blob + P.g.bias[l]);
+            const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+            const int c = grp;
+            if (l < kNL - 1) {
+                if (c < P.g.Np[l] / 16) {
                     float z[16];
-                    umma::tmem_ld16(trow, z);
+                    umma::tmem_ld16(trow + c * 16, z);
                     umma::tmem_ld_wait();
-                    if (active) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) { const float zz = z[i] + bias[c * 16 + i]; z[i] = zz * gelu_eval(zz).cdf; }
+                    store8(s_a, s_a + kATileBytes, row, 2 * c, z);
+                    store8(s_a, s_a + kATileBytes, row, 2 * c + 1, z + 8);
+                }
+            } else if (grp == 0) {
+                float z[16];
+                umma::tmem_ld16(trow, z);
+                umma::tmem_ld_wait();
+                bool need = !active && s_flag[0] == 0;         // empty slot: try the queue again unless it is known to be drained
+                if (active) {
+                    const int ray = s_ray[row];
+                    float px = x[0], py = x[1], pz = x[2];
+                    bool done = true, conv = false;
+                    if (Q.nr_iters > 0) {
                         const float sdf = z[0] + bias3[0];
-                        const float dx = dirs[(size_t)n * 3], dy = dirs[(size_t)n * 3 + 1], dz = dirs[(size_t)n * 3 + 2];
-                        float px = __fadd_rn(x[0], __fmul_rn(__fmul_rn(dx, sdf), Q.sdf_mult));
-                        float py = __fadd_rn(x[1], __fmul_rn(__fmul_rn(dy, sdf), Q.sdf_mult));
-                        float pz = __fadd_rn(x[2], __fmul_rn(__fmul_rn(dz, sdf), Q.sdf_mult));
+                        const float dx = s_dir[row * 3], dy = s_dir[row * 3 + 1], dz = s_dir[row * 3 + 2];
+                        px = __fadd_rn(x[0], __fmul_rn(__fmul_rn(dx, sdf), Q.sdf_mult));
+                        py = __fadd_rn(x[1], __fmul_rn(__fmul_rn(dy, sdf), Q.sdf_mult));
+                        pz = __fadd_rn(x[2], __fmul_rn(__fmul_rn(dz, sdf), Q.sdf_mult));
                         const bool newly = fabsf(sdf) < Q.conv_thresh;
                         bool within;
                         if (Q.has_occ) within = psdf::occ_advance_to_next_occupied(Q.grid, occ, px, py, pz, dx, dy, dz);
@@ -362,23 +380,48 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
                             const float qx = __fsub_rn(px, Q.sph_cx), qy = __fsub_rn(py, Q.sph_cy), qz = __fsub_rn(pz, Q.sph_cz);
                             within = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz))) < Q.sph_radius;
                         }
+                        conv = newly || !within;
+                        const int it = s_it[row] + 1;
+                        s_it[row] = it;
+                        done = conv || it >= Q.nr_iters;
+                    }
+                    if (done) {
+                        pos_out[(size_t)ray * 3] = px; pos_out[(size_t)ray * 3 + 1] = py; pos_out[(size_t)ray * 3 + 2] = pz;
+                        if (converged_out) converged_out[ray] = (uint8_t)conv;
+                        need = true;
+                    } else {
                         s_pos[row * 3] = px; s_pos[row * 3 + 1] = py; s_pos[row * 3 + 2] = pz;
-                        if (newly || !within) s_conv[row] = 1;
                     }
                 }
-                umma::fence_before_sync();
-            }
-            __syncthreads();      // positions / flags of this iteration visible, TMEM reads done
-        }
-        __syncthreads();
-        if (grp == 0 && valid) {
+                // refill: one atomicAdd per warp for all its free slots
+                const unsigned want = __ballot_sync(0xffffffffu, need);
+                if (want) {
+                    int base = 0;
+                    if (lane == __ffs(want) - 1) base = atomicAdd(queue, __popc(want));
+                    base = __shfl_sync(0xffffffffu, base, __ffs(want) - 1);
+                    if (need) {
+                        const int nr = first_queued + base + __popc(want & ((1u << lane) - 1u));
+                        if (nr < P.N) {
 #pragma unroll
-            for (int i = 0; i < 3; i++) pos_out[(size_t)n * 3 + i] = s_pos[row * 3 + i];
-            if (converged_out) converged_out[n] = (uint8_t)(s_conv[row] != 0);
+                            for (int i = 0; i < 3; i++) {
+                                s_pos[row * 3 + i] = pos_in[(size_t)nr * 3 + i];
+                                s_dir[row * 3 + i] = dirs[(size_t)nr * 3 + i];
+                            }
+                            s_ray[row] = nr;
+                            s_it[row] = 0;
+                        } else {
+                            s_ray[row] = -1;
+                            s_flag[0] = 1;
+                        }
+                    }
+                }
+            }
+            umma::fence_before_sync();
         }
-        __syncthreads();
+        __syncthreads();      // slots of this iteration visible, TMEM reads done
     }
     __syncthreads();
+    if (tid == 0 && evaluations) atomicAdd(queue + 1, evaluations);     // statistics: total network evaluations of the launch
     if (warp == 0) umma::tmem_dealloc(tmem_base, 64);
 }
 
@@ -520,7 +563,8 @@ int psdf_sdf_sphere_trace(int N, int L, int T, const float* pos, const float* di
                           const float* shift, const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob,
                           int nr_iters, float sdf_multiplier, float sdf_converged_tresh, const uint8_t* occupancy, int V, float extent,
                           const float trans[3], float sphere_radius, const float sphere_center[3], float* pos_out, uint8_t* converged,
-                          void* stream) {
+                          int* queue_counter, void* stream) {
+    if (!queue_counter) return PSDF_ERR_ARG;
     if (N < 0 || L < 1 || L > kMaxLevels || (L % 4) != 0 || hidden > 64 || hidden % 16 != 0 || out_dim > 64 || nr_iters < 0)
         return PSDF_ERR_UNSUPPORTED;
     if (N == 0) return PSDF_OK;
@@ -540,12 +584,11 @@ int psdf_sdf_sphere_trace(int N, int L, int T, const float* pos, const float* di
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + kTile * 4 * sizeof(float) + 64;
-    static bool attr_done = false;
-    if (!attr_done) { cudaFuncSetAttribute(k_sdf_sphere_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_done = true; }
+    const size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + kTile * 8 * sizeof(float) + 96;
+    cudaFuncSetAttribute(k_sdf_sphere_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     const int ntiles = div_up(N, kTile);
     k_sdf_sphere_trace<<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, Q, pos, dirs, reinterpret_cast<const float2*>(lattice), scale_factor,
-                                                                     shift, window, blob, occupancy, pos_out, converged);
+                                                                     shift, window, blob, occupancy, pos_out, converged, queue_counter);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }

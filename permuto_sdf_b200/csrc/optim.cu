@@ -14,8 +14,10 @@ using namespace psdf;
 namespace {
 __global__ void __launch_bounds__(256)
 k_adamw(long long n, float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, float lr,
-        float beta1, float beta2, float eps, float weight_decay, float bias_c1, float bias_c2_sqrt, const int* __restrict__ step_dev, float grad_scale, int zero_grad) {
+        float beta1, float beta2, float eps, float weight_decay, float bias_c1, float bias_c2_sqrt, const int* __restrict__ step_dev,
+        const float* __restrict__ hyper_dev, float grad_scale, int zero_grad) {
     const long long n4 = n >> 2;
+    if (hyper_dev) { lr = hyper_dev[0]; weight_decay = hyper_dev[1]; }   // schedule values kept in device memory (CUDA-graph replay)
     if (step_dev) {   // step count kept in device memory (CUDA-graph replay): bias corrections computed here
         const float t = (float)step_dev[0];
         bias_c1 = 1.0f - powf(beta1, t);
@@ -73,7 +75,8 @@ k_adamw(long long n, float* __restrict__ p, float* __restrict__ g, float* __rest
 extern "C" {
 // step >= 1 is the (already incremented) step count, read from step_dev[0] instead when that is not NULL; pointers 16-byte aligned
 int psdf_adamw_step(long long n, float* param, float* grad, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, int step, const int* step_dev, float grad_scale, int zero_grad, void* stream) {
+                    float eps, float weight_decay, int step, const int* step_dev, const float* hyper_dev, float grad_scale, int zero_grad,
+                    void* stream) {
     if (n <= 0) return n == 0 ? PSDF_OK : PSDF_ERR_ARG;
     if (step < 1 && !step_dev) return PSDF_ERR_ARG;
     if (step < 1) step = 1;
@@ -88,7 +91,7 @@ int psdf_adamw_step(long long n, float* param, float* grad, float* exp_avg, floa
     if (blocks < 1) blocks = 1;
     if (blocks > sms * 8) blocks = sms * 8;
     k_adamw<<<blocks, 256, 0, ST>>>(n, param, grad, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, (float)c1, (float)sqrt(c2),
-                                   step_dev, grad_scale, zero_grad);
+                                   step_dev, hyper_dev, grad_scale, zero_grad);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }

@@ -118,6 +118,8 @@ def _fused_sdf_sphere_trace(self, points, dirs, iter_nr, nr_iters, sdf_multiplie
     N = pts.shape[0]
     out = torch.empty_like(pts)
     conv = torch.empty(N, dtype=torch.bool, device=pts.device)
+    queue = torch.zeros(2, dtype=torch.int32, device=pts.device)        # [0] ray queue of the persistent CTAs, [1] evaluation count
+    self.last_trace_stats = queue
     window = m.window(iter_nr).view(-1).contiguous()
     sph = m.boundary_primitive
     if occupancy_grid is not None:
@@ -128,7 +130,7 @@ def _fused_sdf_sphere_trace(self, points, dirs, iter_nr, nr_iters, sdf_multiplie
     with torch.no_grad():
         call("psdf_sdf_sphere_trace", N, enc.nr_levels, enc.capacity, pts, drs, enc.lattice_values.detach(), enc.scale_factor, enc.shift_tensor(),
              window, enc.concat_points_scaling, self.hidden, self.out_dim, self.blob, int(nr_iters), float(sdf_multiplier),
-             float(sdf_converged_tresh), occ, V, e, t, float(sph.m_radius), sph.m_center, out, conv)
+             float(sdf_converged_tresh), occ, V, e, t, float(sph.m_radius), sph.m_center, out, conv, queue)
     return out, conv
 
 

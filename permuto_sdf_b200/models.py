@@ -129,6 +129,10 @@ class LipshitzMLP(torch.nn.Module):
             leaky_relu_init(l, negative_slope=0.0)
         if last_layer_linear:
             leaky_relu_init(self.layers[-1], negative_slope=1.0)
+        # the reference registers every weight / bias a second time (models.py:75-79), so its checkpoints carry the keys
+        # mlp.weights_per_layer.N / mlp.biases_per_layer.N next to mlp.layers.N.*; same Parameter objects, same keys here
+        self.weights_per_layer = torch.nn.ParameterList([l.weight for l in self.layers])
+        self.biases_per_layer = torch.nn.ParameterList([l.bias for l in self.layers])
         self.lipshitz_bound_per_layer = torch.nn.ParameterList()
         for l in self.layers:
             max_w = torch.max(torch.sum(torch.abs(l.weight), dim=1))
@@ -162,8 +166,29 @@ class LipshitzMLP(torch.nn.Module):
         return x
 
 
-class SDF(torch.nn.Module):
+class _Checkpointed:
+    """save() of the reference models (models.py:296-307, 393-404, 553-563, 731-741): <ckpt>/<experiment>/<iter>/models/<file>"""
+    checkpoint_file = "model.pt"
+
+    def path_to_save_model(self, ckpt_folder, experiment_name, iter_nr):
+        import os
+        return os.path.join(ckpt_folder, experiment_name, str(iter_nr), "models")
+
+    def save(self, ckpt_folder, experiment_name, iter_nr, additional_name=None):
+        import os
+        models_path = self.path_to_save_model(ckpt_folder, experiment_name, iter_nr)
+        os.makedirs(models_path, exist_ok=True)
+        name = self.checkpoint_file
+        if additional_name:
+            stem, ext = os.path.splitext(name)
+            name = stem + str(additional_name) + ext
+        torch.save(self.state_dict(), os.path.join(models_path, name))
+        return models_path
+
+
+class SDF(torch.nn.Module, _Checkpointed):
     """models.py:131-307"""
+    checkpoint_file = "sdf_model.pt"
 
     def __init__(self, in_channels, boundary_primitive, geom_feat_size_out, nr_iters_for_c2f, nr_levels=24, capacity=2 ** 18,
                  hidden=32, nr_hidden_layers=3):
@@ -263,8 +288,9 @@ class SDF(torch.nn.Module):
         return CurvatureLossFn.apply(sdf_gradients, grads_shifted, nr_valid_dev)
 
 
-class RGB(torch.nn.Module):
+class RGB(torch.nn.Module, _Checkpointed):
     """models.py:309-420"""
+    checkpoint_file = "rgb_model.pt"
 
     def __init__(self, in_channels, boundary_primitive, geom_feat_size_in, nr_iters_for_c2f, nr_levels=24, capacity=2 ** 18,
                  channels=(128, 128, 64, 3)):
@@ -324,8 +350,9 @@ class RGB(torch.nn.Module):
         return [p for n, p in self.named_parameters() if "lattice_values" not in n]
 
 
-class NerfHash(torch.nn.Module):
+class NerfHash(torch.nn.Module, _Checkpointed):
     """models.py:425-563 (background model on the 4-D NeRF++ parametrisation)"""
+    checkpoint_file = "nerf_hash_model.pt"
 
     def __init__(self, in_channels, boundary_primitive, nr_iters_for_c2f, nr_levels=24, capacity=2 ** 18):
         super().__init__()
@@ -360,8 +387,9 @@ class NerfHash(torch.nn.Module):
         return torch.sigmoid(rgb), density
 
 
-class Colorcal(torch.nn.Module):
+class Colorcal(torch.nn.Module, _Checkpointed):
     """models.py:677-741: per-image affine colour calibration, image `idx_with_fixed_calib` stays identity"""
+    checkpoint_file = "colorcal_model.pt"
 
     def __init__(self, nr_cams, idx_with_fixed_calib):
         super().__init__()

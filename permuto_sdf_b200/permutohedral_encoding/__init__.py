@@ -35,7 +35,11 @@ class _EncodeFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         lattice, positions, window = ctx.saved_tensors
         need_l, need_p = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        g_l, g_p = _EncodeBackFn.apply(lattice, positions, window, grad_out.contiguous(), ctx.mod, need_l, need_p)
+        # needs_input_grad is static: torch.autograd.grad(sdf, points, create_graph=True) (models.py:245-251) also reports the
+        # lattice as "needed" although its gradient is discarded. Only a backward that runs with grad mode off (loss.backward())
+        # may therefore scatter straight into lattice.grad; under create_graph the table gradient goes to a scratch buffer.
+        allow_in_place = not torch.is_grad_enabled()
+        g_l, g_p = _EncodeBackFn.apply(lattice, positions, window, grad_out.contiguous(), ctx.mod, need_l, need_p, allow_in_place)
         if need_l and g_l.numel() == 1 and lattice.numel() != 1:
             g_l = None          # already accumulated into lattice.grad (grad_in_place)
         return (g_l if need_l else None), (g_p if need_p else None), None, None
@@ -43,11 +47,12 @@ class _EncodeFn(torch.autograd.Function):
 
 class _EncodeBackFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, lattice, positions, window, grad_out, mod, need_l, need_p):
+    def forward(ctx, lattice, positions, window, grad_out, mod, need_l, need_p, allow_in_place=True):
         D, L, F, T = _enc_consts(mod)
         N = positions.shape[0]
         # grad_in_place (flat-buffer optimizer): scatter straight into lattice.grad instead of a fresh zero-filled table
-        in_place = need_l and getattr(mod, "grad_in_place", False) and lattice.grad is not None and lattice.grad.is_contiguous()
+        in_place = need_l and allow_in_place and getattr(mod, "grad_in_place", False) and lattice.grad is not None and \
+            lattice.grad.is_contiguous()
         g_l = (lattice.grad if in_place else torch.zeros_like(lattice)) if need_l else None
         g_p = torch.empty_like(positions) if need_p else None
         call("psdf_enc_backward", N, D, L, F, T, positions, lattice, mod.scale_factor, mod.shift_tensor(), window,
@@ -76,7 +81,7 @@ class _EncodeBackFn(torch.autograd.Function):
             g_go = torch.empty_like(grad_out) if need_go else None
             call("psdf_enc_double_backward", N, D, L, F, T, positions, lattice, mod.scale_factor, mod.shift_tensor(), window,
                  1 if mod.concat_points else 0, mod.concat_points_scaling, gg_pos.contiguous(), grad_out, g_l, g_go)
-        return g_l, None, None, g_go, None, None, None
+        return g_l, None, None, g_go, None, None, None, None
 
 
 class PermutoEncoding(torch.nn.Module):
@@ -106,7 +111,8 @@ class PermutoEncoding(torch.nn.Module):
         shift = torch.randn(self.nr_levels, self.pos_dim) * 10.0 if self.apply_random_shift_per_level else torch.zeros(
             self.nr_levels, self.pos_dim)
         self.random_shift_per_level = torch.nn.Parameter(shift.to(dev), requires_grad=False)
-        self.register_buffer("scale_factor", self.compute_scale_factor(self.scale_per_level, self.pos_dim).to(dev))
+        # derived from scale_per_level, not state: kept out of state_dict (upstream checkpoints hold lattice_values + random shift only)
+        self.register_buffer("scale_factor", self.compute_scale_factor(self.scale_per_level, self.pos_dim).to(dev), persistent=False)
         self._ones = None
         self.grad_in_place = False      # True: backward scatters into lattice_values.grad directly (set by the flat-buffer optimizer path)
 

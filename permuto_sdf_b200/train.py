@@ -46,6 +46,27 @@ class HyperParams:
     background_nr_iters_for_c2f = 1
     target_nr_of_samples = 512 * (64 + 16 + 16)
     with_mask = True
+    # schedules of the reference loop (train_permuto_sdf.py:89-90,304,395-405,417-421)
+    lr_milestones = (100000, 150000, 180000, 190000)
+    lr_decay_gamma = 0.3
+    lr_warmup_iters = 3000
+    use_lr_schedule = True           # GradualWarmupScheduler(multiplier=1, total_epoch=3000) -> MultiStepLR(gamma=0.3)
+    eikonal_weight_late = 0.01       # eikonal weight once iter >= iter_start_reduce_curv (:405)
+    rgb_encoding_wd_late = 1.0       # weight decay of model_rgb_only_encoding from the same iteration on (:400-403)
+    adaptive_nr_rays = False         # nr_rays_to_create *= target_nr_of_samples / cur_nr_samples (:395-397); needs a host read per iteration
+    nr_rays_bucket = 64              # adaptive ray counts are rounded to this multiple (bounded set of shapes / captured graphs)
+
+
+def lr_schedule(hp, it):
+    """learning rate used by optimizer.step() of (post-sphere-init) iteration `it` in the reference: the warm-up scheduler is
+    created after the step of iteration 0 and stepped once per iteration (train_permuto_sdf.py:417-421), so iteration it >= 1
+    runs with the value after `it` scheduler steps: base * it / 3000 up to 3000, then MultiStepLR counted from step 3001."""
+    if not hp.use_lr_schedule or it <= 0:
+        return hp.lr
+    if it <= hp.lr_warmup_iters:
+        return hp.lr * float(it) / hp.lr_warmup_iters
+    epoch = it - (hp.lr_warmup_iters + 1)
+    return hp.lr * hp.lr_decay_gamma ** sum(1 for m in hp.lr_milestones if epoch >= m)
 
 
 def create_samples(with_mask, hyperparams, ray_origins, ray_dirs, jitter_samples, occupancy_grid, bounding_primitive):
@@ -244,6 +265,44 @@ def run_net_sphere_traced(ray_origins, ray_dirs, hyperparams, model_sdf, model_r
     return pred_rgb, pred_normals, pred_weights_sum
 
 
+def load_from_checkpoint(ckpt_path_full, model_sdf, model_rgb, model_bg, occupancy_grid, model_colorcal=None):
+    """permuto_sdf_utils.py:222-237: <ckpt_path_full>/{sdf_model,rgb_model,nerf_hash_model_bg}.pt + grid_values.pt /
+    grid_occupancy.pt, the files train_permuto_sdf.py:444-453 writes (same key names, so reference checkpoints load here and
+    ours load there). Models that are None (no background network with --with_mask) are skipped."""
+    import os
+    dev = next(model_sdf.parameters()).device
+    ld = lambda name: torch.load(os.path.join(ckpt_path_full, name), map_location=dev)
+    model_sdf.load_state_dict(ld("sdf_model.pt"))
+    model_rgb.load_state_dict(ld("rgb_model.pt"))
+    if model_bg is not None and os.path.exists(os.path.join(ckpt_path_full, "nerf_hash_model_bg.pt")):
+        model_bg.load_state_dict(ld("nerf_hash_model_bg.pt"))
+    if model_colorcal is not None and os.path.exists(os.path.join(ckpt_path_full, "colorcal_model.pt")):
+        model_colorcal.load_state_dict(ld("colorcal_model.pt"))
+    for m in (model_sdf, model_rgb, model_bg):
+        if m is not None:
+            m.eval()
+    if occupancy_grid is not None and os.path.exists(os.path.join(ckpt_path_full, "grid_values.pt")):
+        occupancy_grid.set_grid_values(ld("grid_values.pt"))
+        occupancy_grid.set_grid_occupancy(ld("grid_occupancy.pt"))
+
+
+def run_net_in_chunks(ray_origins_full, ray_dirs_full, chunk_size, with_mask, hyperparams, model_sdf, model_rgb, model_bg, occupancy_grid,
+                      iter_nr_for_anneal, cos_anneal_ratio, forced_variance):
+    """train_permuto_sdf.py:172-209 without the frame -> rays / image reshapes: volume-render a full image chunk by chunk.
+    -> (pred_rgb [R,3], pred_rgb_bg [R,3] or None, pred_normals [R,3], pred_weights_sum [R,1])"""
+    nr_chunks = max(1, math.ceil(ray_origins_full.shape[0] / chunk_size))
+    rgb_l, bg_l, nrm_l, ws_l = [], [], [], []
+    with torch.no_grad():
+        for o, d in zip(torch.chunk(ray_origins_full, nr_chunks), torch.chunk(ray_dirs_full, nr_chunks)):
+            pred_rgb, pred_rgb_bg, pred_normals, _, weights_sum, _ = run_net(with_mask, hyperparams, o.contiguous(), d.contiguous(), None,
+                                                                             model_sdf, model_rgb, model_bg, None, occupancy_grid,
+                                                                             iter_nr_for_anneal, cos_anneal_ratio, forced_variance)
+            rgb_l.append(pred_rgb.detach()); nrm_l.append(pred_normals.detach()); ws_l.append(weights_sum.detach())
+            if pred_rgb_bg is not None:
+                bg_l.append(pred_rgb_bg.detach())
+    return torch.cat(rgb_l, 0), (torch.cat(bg_l, 0) if bg_l else None), torch.cat(nrm_l, 0), torch.cat(ws_l, 0)
+
+
 class Trainer:
     """State of one PermutoSDF training run on synthetic data (models, occupancy grid, optimizer) and the
     per-iteration step of train_permuto_sdf.py:311-422 (after sphere init), with `--with_mask` semantics."""
@@ -261,14 +320,18 @@ class Trainer:
         self.model_bg = None if hp.with_mask else NerfHash(4, self.aabb, hp.background_nr_iters_for_c2f, nr_levels, capacity).to("cuda")
         self.model_colorcal = Colorcal(nr_images, 0) if (hp.use_color_calibration and with_colorcal) else None
         self.occupancy_grid = OccupancyGrid(occupancy_resolution, 1.0, [0, 0, 0]) if hp.use_occupancy_grid else None
-        if fused_inference and nr_levels % 4 == 0 and sdf_hidden % 16 == 0 and sdf_hidden <= 64 and self.model_sdf.encoding.output_dims() <= 64:
+        # No silent fall-back: asking for the fused (tcgen05) path with a shape it does not cover raises here (FusedSDF / FusedRGB
+        # say which constraint failed); the per-op path is only taken when the caller asks for it (fused_inference=False /
+        # fused_training=False). `self.execution` records which path each model runs on.
+        self.execution = {"sdf_inference": "per-op kernels", "sdf_training": "per-op kernels + autograd", "rgb": "per-op kernels + autograd",
+                          "background": "per-op kernels + autograd" if self.model_bg is not None else None}
+        if fused_inference:
             self.model_sdf.enable_fused_inference()
+            self.execution["sdf_inference"] = "fused tcgen05"
             if fused_training:
                 self.model_sdf.enable_fused_training()
-                try:                                  # colour network on the tensor cores when its shape fits the fused kernels
-                    self.model_rgb.enable_fused()
-                except RuntimeError:
-                    pass
+                self.model_rgb.enable_fused()
+                self.execution["sdf_training"] = self.execution["rgb"] = "fused tcgen05"
         groups = [{"params": list(self.model_sdf.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_sdf"}]
         if self.model_bg is not None:
             groups.append({"params": list(self.model_bg.parameters()), "weight_decay": 0.0, "lr": hp.lr, "name": "model_bg"})
@@ -290,6 +353,41 @@ class Trainer:
         self._cg = None                 # CUDA-graph state (enable_cuda_graph)
         self.nr_rays_to_create = hp.nr_rays
         self.last = {}
+
+    def save(self, ckpt_folder, experiment_name, iter_nr=None, with_optimizer=True):
+        """train_permuto_sdf.py:444-453: every model's state_dict + the occupancy grid under <ckpt>/<experiment>/<iter>/models/;
+        additionally (not in the reference) the optimizer moments and iteration number, so that a run resumes bit for bit"""
+        import os
+        it = self.iter_nr if iter_nr is None else iter_nr
+        path = self.model_sdf.save(ckpt_folder, experiment_name, it)
+        self.model_rgb.save(ckpt_folder, experiment_name, it)
+        if self.model_bg is not None:
+            self.model_bg.save(ckpt_folder, experiment_name, it, additional_name="_bg")
+        if self.model_colorcal is not None:
+            self.model_colorcal.save(ckpt_folder, experiment_name, it)
+        if self.occupancy_grid is not None:
+            torch.save(self.occupancy_grid.get_grid_values(), os.path.join(path, "grid_values.pt"))
+            torch.save(self.occupancy_grid.get_grid_occupancy(), os.path.join(path, "grid_occupancy.pt"))
+        if with_optimizer:
+            torch.save({"optimizer": self.optimizer.state_dict(), "iter_nr": self.iter_nr,
+                        "nr_rays_to_create": self.nr_rays_to_create}, os.path.join(path, "trainer_state.pt"))
+        return path
+
+    def load(self, ckpt_path_full, with_optimizer=True):
+        """inverse of save(); also reads checkpoints written by the reference (no trainer_state.pt: models + grid only).
+        Parameters are copied into the existing storages, so the flat-buffer optimizer's views stay valid."""
+        import os
+        load_from_checkpoint(ckpt_path_full, self.model_sdf, self.model_rgb, self.model_bg, self.occupancy_grid, self.model_colorcal)
+        st = os.path.join(ckpt_path_full, "trainer_state.pt")
+        if with_optimizer and os.path.exists(st):
+            sd = torch.load(st, map_location=next(self.model_sdf.parameters()).device)
+            self.optimizer.load_state_dict(sd["optimizer"])
+            self.iter_nr = int(sd["iter_nr"])
+            self.nr_rays_to_create = int(sd.get("nr_rays_to_create", self.nr_rays_to_create))
+        if getattr(self.model_sdf, "fused", None) is not None:
+            self.model_sdf.fused.repack()           # load_state_dict copies in place
+        if self._cg is not None:
+            self._cg["it_host"] = None              # device-resident iteration number is refreshed on the next step
 
     def set_analytic_scene(self, object_radius=0.3, inv_s=512.0):
         """occupancy of the analytic sphere SDF ||x|| - r through update_with_sdf"""
@@ -350,6 +448,32 @@ class Trainer:
                          nr_samples=fg.samples_pos.shape[0], nr_samples_dev=fg.cur_nr_samples, fg=fg)
         return loss
 
+    def apply_schedules(self, it):
+        """host-side schedule edits of one iteration, run between the loss and the optimizer step like the reference does
+        (train_permuto_sdf.py:395-405,417-421): LR warm-up / decay, weight decay 1.0 on the colour hash table and eikonal weight
+        0.01 once iter >= iter_start_reduce_curv (the new eikonal weight is seen by the NEXT iteration's loss, as in the reference,
+        where the edit follows the loss computation). In CUDA-graph mode lr / weight decay reach the kernel through
+        FusedAdamW.hyper_dev and the eikonal weight is part of the forward/backward graph's cache key."""
+        hp = self.hp
+        lr = lr_schedule(hp, it)
+        late = it >= hp.iter_start_reduce_curv
+        for g in self.optimizer.param_groups:
+            g["lr"] = lr
+            if late and g.get("name") == "model_rgb_only_encoding":
+                g["weight_decay"] = hp.rgb_encoding_wd_late
+        if late:
+            hp.eikonal_weight = hp.eikonal_weight_late
+
+    def adapt_nr_rays(self, cur_nr_samples):
+        """train_permuto_sdf.py:395-397; the count is bucketed so that CUDA-graph mode sees a bounded set of ray counts"""
+        hp = self.hp
+        if not hp.adaptive_nr_rays or cur_nr_samples <= 0:
+            return self.nr_rays_to_create
+        n = int(self.nr_rays_to_create * float(hp.target_nr_of_samples) / cur_nr_samples)
+        b = max(int(hp.nr_rays_bucket), 1)
+        self.nr_rays_to_create = max(b, (n + b // 2) // b * b)
+        return self.nr_rays_to_create
+
     def update_occupancy(self, iter_nr_for_anneal):
         """train_permuto_sdf.py:386-391 (every 8th iteration)"""
         with torch.no_grad():
@@ -368,6 +492,9 @@ class Trainer:
             update_occupancy = (it % 8 == 0)
         if update_occupancy and self.hp.use_occupancy_grid:
             self.update_occupancy(it)
+        if self.hp.adaptive_nr_rays:
+            self.adapt_nr_rays(int(self.last["nr_samples"]))
+        self.apply_schedules(it)
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
         if optimizer_step:
@@ -390,6 +517,7 @@ class Trainer:
         opt.device_step = True
         dev = opt.flat_param.device
         opt.step_dev = torch.full((1,), opt.step_count, dtype=torch.int32, device=dev)
+        opt.sync_hyper()
         self._cg = dict(warm=int(warmup_steps), fb=None, opt={}, it_dev=torch.zeros((), device=dev), it_host=None,
                         stream=torch.cuda.Stream(device=dev), launches=0)
 
@@ -430,7 +558,10 @@ class Trainer:
         self._sync_device_iter()
         # with make_rays the graph inputs are (pixel indices, image indices) and ray generation is captured with the iteration
         inputs = [ray_origins, ray_dirs] if make_rays is not None else [ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices]
-        shapes = (make_rays is not None,) + tuple(None if t is None else (tuple(t.shape), t.dtype) for t in inputs)
+        hp = self.hp
+        # by-value constants of the captured kernels: a schedule edit (eikonal 0.04 -> 0.01 at iter_start_reduce_curv) re-captures
+        consts = (hp.eikonal_weight, hp.curvature_weight, hp.mask_weight, hp.offsurface_weight, hp.lipshitz_weight)
+        shapes = (make_rays is not None, consts) + tuple(None if t is None else (tuple(t.shape), t.dtype) for t in inputs)
         fb = cg["fb"]
         valid = fb is not None and fb["shapes"] == shapes and fb["lo"] <= it < fb["hi"]
         cur = torch.cuda.current_stream()
@@ -455,6 +586,7 @@ class Trainer:
             for dst, src in zip(fb["static"], inputs):
                 if dst is not None:
                     dst.copy_(src, non_blocking=True)
+            self.optimizer.zero_grad(set_to_none=False)     # no-op unless a previous iteration skipped its optimizer step
             fb["graph"].replay()
             self.last = fb["last"]
             loss = fb["loss"]
@@ -465,6 +597,9 @@ class Trainer:
             update_occupancy = (it % 8 == 0)
         if update_occupancy and self.hp.use_occupancy_grid:
             self.update_occupancy(it)
+        if self.hp.adaptive_nr_rays:
+            self.adapt_nr_rays(int(self.last["nr_samples_dev"].item()))     # the reference's loop reads the count every iteration too
+        self.apply_schedules(it)
         if optimizer_step:
             self.optimizer_step()
         self.iter_nr += 1
@@ -496,6 +631,7 @@ class Trainer:
         cg = self._cg
         if allreduce:
             import torch.distributed as dist
+        self.optimizer.sync_hyper()     # lr / weight_decay edits since the last replay -> device (outside any capture)
         if cg["fb"] is None:            # still in the eager warm-up iterations
             side, cur = cg["stream"], torch.cuda.current_stream()
             side.wait_stream(cur)

@@ -64,3 +64,64 @@ def test_splitk_weight_gradient_matches_plain_gemm():
     torch.nn.functional.linear(x, w, bias).pow(2).sum().backward()
     for a, t in zip(g, (x, w, bias)):
         assert torch.allclose(a, t.grad, rtol=1e-10, atol=1e-10)
+
+
+def test_lr_schedule_matches_warmup_then_multistep():
+    """GradualWarmupScheduler(multiplier=1, total_epoch=3000, after_scheduler=MultiStepLR(milestones, gamma=0.3)) as driven by
+    train_permuto_sdf.py:417-421, replayed with torch's own MultiStepLR and the reference's warm-up rule"""
+    from permuto_sdf_b200.train import HyperParams, lr_schedule
+    hp = HyperParams()
+    hp.lr_milestones = (40, 70)
+    hp.lr_warmup_iters = 10
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.SGD([p], lr=hp.lr)
+    decay = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=list(hp.lr_milestones), gamma=hp.lr_decay_gamma)
+    # iteration 0 steps with the base lr; the warm-up scheduler is created afterwards (lr -> 0) and stepped once per iteration
+    used = [hp.lr]
+    last_epoch, finished = 0, False
+    for it in range(1, 120):
+        last_epoch += 1
+        if finished:
+            decay.step()
+            lr = decay.get_last_lr()[0]
+        elif last_epoch > hp.lr_warmup_iters:
+            finished = True
+            lr = decay.get_last_lr()[0]
+        else:
+            lr = hp.lr * last_epoch / hp.lr_warmup_iters
+        used.append(lr)
+    for it, want in enumerate(used):
+        assert lr_schedule(hp, it) == pytest.approx(want, rel=1e-12), it
+    hp.use_lr_schedule = False
+    assert lr_schedule(hp, 5) == hp.lr
+
+
+def test_checkpoint_keys_match_reference_models(tmp_path):
+    """state_dict key names of the reference's classes (models.py:75-79,149-161,330-340,449-470; SingleVarianceNetwork
+    volume_rendering_modules.py:95) so that checkpoints written by either side load on the other; save() file layout of
+    models.py:296-307"""
+    import os
+    from permuto_sdf_b200.models import RGB, SDF, Colorcal, NerfHash
+    sdf = SDF(3, None, 32, 1000, nr_levels=4, capacity=2 ** 8)
+    rgb = RGB(3, None, 32, 1, nr_levels=4, capacity=2 ** 8)
+    bg = NerfHash(4, None, 1, nr_levels=4, capacity=2 ** 8)
+    cal = Colorcal(3, 0)
+    ks = set(sdf.state_dict())
+    assert ks == {"encoding.lattice_values", "encoding.random_shift_per_level"} | {"mlp_sdf.%d.%s" % (i, n) for i in (0, 2, 4, 6) for n in ("weight", "bias")}
+    kr = set(rgb.state_dict())
+    want = {"volume_renderer_neus.deviation_network.variance", "encoding.lattice_values", "encoding.random_shift_per_level"}
+    want |= {"mlp.layers.%d.%s" % (i, n) for i in range(4) for n in ("weight", "bias")}
+    want |= {"mlp.%s.%d" % (n, i) for i in range(4) for n in ("weights_per_layer", "biases_per_layer", "lipshitz_bound_per_layer")}
+    assert kr == want
+    assert rgb.mlp.weights_per_layer[2] is rgb.mlp.layers[2].weight          # the same Parameter, registered twice like the reference
+    assert len(list(rgb.parameters())) == 1 + 1 + 1 + 8 + 4                   # no duplicates reach the optimizer
+    kb = set(bg.state_dict())
+    assert {"mlp_feat_and_density.6.weight", "mlp_rgb.4.bias", "encoding.lattice_values"} <= kb
+    assert set(cal.state_dict()) == {"weight_delta", "bias"}
+    path = sdf.save(str(tmp_path), "exp", 300)
+    rgb.save(str(tmp_path), "exp", 300); bg.save(str(tmp_path), "exp", 300, additional_name="_bg"); cal.save(str(tmp_path), "exp", 300)
+    assert path == os.path.join(str(tmp_path), "exp", "300", "models")
+    assert sorted(os.listdir(path)) == ["colorcal_model.pt", "nerf_hash_model_bg.pt", "rgb_model.pt", "sdf_model.pt"]
+    sdf2 = SDF(3, None, 32, 1000, nr_levels=4, capacity=2 ** 8)
+    sdf2.load_state_dict(torch.load(os.path.join(path, "sdf_model.pt")))
+    assert all(torch.equal(a, b) for a, b in zip(sdf.state_dict().values(), sdf2.state_dict().values()))

@@ -270,3 +270,87 @@ def test_iteration_with_background_model(cuda, graph):
     RaySamplesPacked.static_capacity = False
     assert all(np.isfinite(l) for l in losses), losses
     assert not torch.equal(bg0, tr.model_bg.encoding.lattice_values.detach()), "the background model received no gradient"
+
+
+def test_flat_optimizer_with_modular_sdf_path_matches_adamw_gradients(cuda):
+    """optimizer='fused' turns on grad_in_place; on the modular SDF path (fused_training=False) the create_graph backward
+    of get_sdf_and_gradient must NOT scatter d(sum sdf)/d(lattice) into lattice.grad. Gradients of one iteration must equal the
+    ones of the plain torch.optim.AdamW configuration."""
+    from permuto_sdf import PermutoSDF, RaySamplesPacked
+    from permuto_sdf_b200.train import HyperParams, Trainer
+    import test_graph_gpu
+    grads = {}
+    for opt in ("adamw", "fused"):
+        test_graph_gpu._fresh_rngs()
+        hp = HyperParams()
+        hp.max_nr_samples_per_ray = 32
+        hp.nr_samples_imp_sampling = 8
+        hp.min_dist_between_samples = 1e-3
+        hp.offsurface_weight = 0.0
+        tr = Trainer(hp, nr_levels=8, capacity=2 ** 14, sdf_hidden=64, occupancy_resolution=128, nr_images=4, seed=4, optimizer=opt,
+                     fused_training=False, fused_render=False)
+        assert tr.execution["sdf_training"].startswith("per-op")
+        tr.set_analytic_scene()
+        tr.iter_nr = 60000            # past the curvature phase (its random directions come from torch's generator)
+        rgb, mask, K, tf = scenes.synthetic_reel(nimg=4, H=60, W=80)
+
+        class Reel:
+            pass
+        reel = Reel()
+        reel.rgb_reel, reel.mask_reel, reel.K_reel, reel.tf_world_cam_reel = [torch.from_numpy(a).cuda() for a in (rgb, mask, K, tf)]
+        gen = torch.Generator().manual_seed(5)
+        pix = torch.randint(0, 60 * 80, (256,), generator=gen, dtype=torch.int32).cuda()
+        img = torch.randint(0, 4, (256,), generator=gen, dtype=torch.int32).cuda()
+        with torch.no_grad():
+            o, d, gt, gm, idx = PermutoSDF.rays_from_reel_indices(reel, pix, img)
+        tr.step(o, d, gt, gm, idx, update_occupancy=False, optimizer_step=False)
+        grads[opt] = torch.cat([p.grad.detach().reshape(-1).clone() for p in tr.model_sdf.parameters() if p.grad is not None])
+    test_graph_gpu._fresh_rngs()
+    a, b = grads["adamw"], grads["fused"]
+    assert a.shape == b.shape and float(a.norm()) > 0
+    assert float((a - b).norm() / a.norm()) < 1e-3
+
+
+def test_trainer_checkpoint_roundtrip_and_chunked_render(cuda, tmp_path):
+    """f4: Trainer.save writes the reference's file layout (train_permuto_sdf.py:444-453), Trainer.load restores a run exactly
+    (next loss identical), run_net_in_chunks (train_permuto_sdf.py:172-209) equals the one-shot render"""
+    import os
+    from permuto_sdf_b200.train import HyperParams, Trainer, run_net, run_net_in_chunks
+    import test_graph_gpu
+
+    def make():
+        test_graph_gpu._fresh_rngs()
+        hp = HyperParams()
+        hp.max_nr_samples_per_ray = 32
+        hp.nr_samples_imp_sampling = 8
+        hp.min_dist_between_samples = 1e-3
+        tr = Trainer(hp, nr_levels=8, capacity=2 ** 14, sdf_hidden=64, occupancy_resolution=64, nr_images=4, seed=6, optimizer="fused")
+        tr.set_analytic_scene()
+        tr.iter_nr = 60000
+        return tr
+    o, d = scenes.make_rays(256, seed=3)
+    o, d = torch.from_numpy(o).cuda(), torch.from_numpy(d).cuda()
+    gt, gm = torch.rand(256, 3, device="cuda"), torch.ones(256, 1, device="cuda")
+    img = torch.zeros(256, dtype=torch.int32, device="cuda")
+    tr = make()
+    for _ in range(3):
+        tr.step(o, d, gt, gm, img, update_occupancy=True)
+    path = tr.save(str(tmp_path), "run")
+    assert sorted(os.listdir(path)) == ["colorcal_model.pt", "grid_occupancy.pt", "grid_values.pt", "rgb_model.pt", "sdf_model.pt", "trainer_state.pt"]
+    assert path.endswith(os.path.join("run", "60003", "models"))
+    tr2 = make()
+    tr2.load(path)
+    assert tr2.iter_nr == tr.iter_nr and tr2.optimizer.step_count == tr.optimizer.step_count
+    for a, b in zip(tr.params, tr2.params):
+        assert torch.equal(a, b)
+    assert torch.equal(tr.occupancy_grid.get_grid_occupancy(), tr2.occupancy_grid.get_grid_occupancy())
+    # same state -> same evaluation (eval mode: no jitter)
+    for t in (tr, tr2):
+        t.model_sdf.eval(); t.model_rgb.eval()
+    with torch.no_grad():
+        full = [run_net(True, t.hp, o, d, None, t.model_sdf, t.model_rgb, None, None, t.occupancy_grid, 60003, 1.0, 0.8) for t in (tr, tr2)]
+    assert torch.equal(full[0][0], full[1][0])
+    rgb_c, bg_c, nrm_c, ws_c = run_net_in_chunks(o, d, 100, True, tr.hp, tr.model_sdf, tr.model_rgb, None, tr.occupancy_grid, 60003, 1.0, 0.8)
+    assert bg_c is None and rgb_c.shape == (256, 3)
+    assert float((rgb_c - full[0][0]).abs().max()) < 1e-5 and float((ws_c - full[0][4]).abs().max()) < 1e-5
+    test_graph_gpu._fresh_rngs()
