@@ -10,6 +10,9 @@ Workload (BASELINE.json configs[1], "C2"): one training iteration of PermutoSDF 
 (65 536 samples when every ray hits), 16-level permutohedral lattice (2^18 x 2 per level), 3x64 SDF MLP,
 Lipschitz RGB MLP, 256^3 occupancy grid of the analytic sphere SDF |x|-0.3. A step = ray generation, sampling,
 importance resampling, forward, losses, backward through the double backward, dense AdamW.
+  python bench.py --rays 8192 ...                          same step with more rays per GPU (BASELINE config 4 = 8192 rays/GPU x 8 GPUs)
+  python bench.py --workload sphere_trace [--gpus N]       sphere-traced render of one 1920x1080 frame (BASELINE config 5): px/s
+
 Metric: rays/s (whole job). `value`: inputs resident on the device. `e2e`: per step the ray indices come from pinned
 host memory and the loss is read back. Multi-GPU: rays sharded by rank (weak scaling), one NCCL all-reduce of the
 flat gradient buffer per step.
@@ -122,6 +125,7 @@ def central_pixels(n, H, W, box, gen):
 
 
 def run_ours(args):
+    global NR_RAYS
     import torch.distributed as dist
     from permuto_sdf_b200 import _lib, load_library
     from permuto_sdf_b200.dist import FlatGrads
@@ -142,6 +146,7 @@ def run_ours(args):
     hp = HyperParams()
     hp.max_nr_samples_per_ray = SAMPLES_PER_RAY - 2 * 16
     hp.nr_samples_imp_sampling = 16
+    NR_RAYS = int(args.rays)
     hp.nr_rays = NR_RAYS
     tr = Trainer(hp, nr_levels=16, capacity=2 ** 18, sdf_hidden=64, nr_images=8, occupancy_resolution=256, seed=0,
                  fused_inference=not args.modular, fused_training=not args.modular, optimizer="adamw" if args.modular else "fused")
@@ -245,9 +250,8 @@ def run_ours(args):
         "psdf_rgb_fused_backward": 12 + 2 * L * 4 * 8 + 12 + 12 + 128 + 12 + 12 + 128,
     }
     units = dict(_lib.LAST_UNITS)
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-    # (profiles/r1_ncu_fused_kernels.csv; value + tangent variant of the forward kernel)
-    ncu_traffic = {"psdf_sdf_fused_forward": 17.59e6 + 0.23e6, "psdf_sdf_fused_backward": 73.6e6 + 244.4e6}
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the tracked `ncu --set full` capture of this workload
+    ncu_traffic = ncu_traffic_from_profiles()
     roof = None
     if ktimes:
         top = sorted(((v[1], k) for k, v in ktimes.items()), reverse=True)
@@ -270,7 +274,8 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours",
-            "config": {"workload": WORKLOAD, "rays_per_gpu": NR_RAYS, "avg_samples_per_step": avg_samples, "parallelism": "dp%d" % world,
+            "config": {"workload": WORKLOAD if NR_RAYS == 512 else WORKLOAD.replace("512 rays", "%d rays" % NR_RAYS).replace("C2:", "C2 shape at %d rays/GPU (BASELINE config 4 when 8192 x 8 GPUs):" % NR_RAYS),
+                       "rays_per_gpu": NR_RAYS, "avg_samples_per_step": avg_samples, "parallelism": "dp%d" % world,
                        "l2": "per-step working set (2 lattice tables + grads + Adam moments ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
                        "timed_region": "sum of per-step CUDA-event intervals",
                        "execution": "eager" if (args.modular or args.eager) else "CUDA graphs (forward+backward graph, optimizer graph), static-capacity containers"},
@@ -282,6 +287,159 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return out
+
+
+def run_sphere_trace(args):
+    """BASELINE config 5: sphere-traced render (train_permuto_sdf.py:211-242, sdf_utils.py:120-218) of one 1920x1080 frame, 256
+    iterations max, occupancy grid on, normals + colour included. N GPUs: the image is tiled by rows, every rank traces its tile and
+    one NCCL all_gather assembles the frame on all ranks. `value`: camera already on the device, image stays there; `e2e`: camera
+    (K, pose) from pinned host memory, finished image copied back to pinned host memory inside the timed region."""
+    import torch.distributed as dist
+    import permuto_sdf_b200.train as T
+    from permuto_sdf_b200 import _lib, load_library
+    from permuto_sdf_b200.train import HyperParams, Trainer
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert load_library().psdf_device_ok() == 1
+    W, H = args.width, args.height
+    hp = HyperParams()
+    tr = Trainer(hp, nr_levels=16, capacity=2 ** 18, sdf_hidden=64, nr_images=8, occupancy_resolution=256, seed=0, optimizer="fused")
+    tr.set_analytic_scene()
+    m = tr.model_sdf
+    # fit the SDF to the analytic sphere of the scene (the reference's sphere initialisation, train_permuto_sdf.py:262-291): rays then
+    # converge on a surface inside the occupied shell like on a trained model. Same seed on every rank -> identical replicas.
+    for i in range(400):
+        loss, _, _ = T.loss_sphere_init(30000, tr.aabb, m, 20000)
+        tr.optimizer.zero_grad(set_to_none=False)
+        loss.backward()
+        tr.optimizer_step()
+    m.eval(); tr.model_rgb.eval()
+    m.last_iter_nr = 20000
+    torch.set_grad_enabled(False)
+    rows = [(H * r) // world for r in range(world + 1)]
+    r0, r1 = rows[rank], rows[rank + 1]
+    cam_host = torch.tensor([1.2 * W, W / 2.0, H / 2.0, 0.0, 0.0, -1.5], dtype=torch.float32).pin_memory()   # f, cx, cy, camera centre
+    img_host = torch.empty(H, W, 3, dtype=torch.float32).pin_memory()
+    cam_dev = cam_host.to(dev)
+    tile_rows = max(b - a for a, b in zip(rows[:-1], rows[1:]))
+    gathered = torch.zeros(world, tile_rows * W, 3, device=dev)
+    stats = {"evals": 0, "rays": 0}
+
+    def frame(e2e):
+        cam = cam_host.to(dev, non_blocking=True) if e2e else cam_dev
+        # primary rays of this rank's rows (pixel centres; CreateRaysModule of the reference, models/modules.py:170-230). The camera sits on
+        # the -z side looking along +z: rays leave the grid through a POSITIVE face. Rays that leave through a negative face are never
+        # flagged out of bounds by the reference's marcher (float -> uint saturation, SURVEY.md A.2, reproduced bit for bit): they alias
+        # voxel column 0, exhaust the DDA step budget in every iteration and burn all 256 iterations far outside the scene.
+        v, u = torch.meshgrid(torch.arange(r0, r1, device=dev, dtype=torch.float32), torch.arange(W, device=dev, dtype=torch.float32), indexing="ij")
+        d = torch.stack([(u + 0.5 - cam[1]) / cam[0], (v + 0.5 - cam[2]) / cam[0], torch.ones_like(u)], -1).reshape(-1, 3)
+        d = torch.nn.functional.normalize(d, dim=-1).contiguous()
+        o = cam[3:6].expand_as(d).contiguous()
+        rgb, normals, wsum = T.run_net_sphere_traced(o, d, hp, m, tr.model_rgb, tr.occupancy_grid, 20000, args.trace_iters, 0.9, 2e-4)
+        if world > 1:
+            mine = torch.zeros(tile_rows * W, 3, device=dev)
+            mine[: rgb.shape[0]] = rgb
+            dist.all_gather_into_tensor(gathered.view(-1), mine.view(-1))      # the single collective of this path
+            img = torch.cat([gathered[r, : (rows[r + 1] - rows[r]) * W] for r in range(world)], 0)
+        else:
+            img = rgb
+        if e2e:
+            img_host.view(-1, 3).copy_(img, non_blocking=True)
+        return img
+
+    def timed(e2e, with_events):
+        for _ in range(args.warmup):
+            frame(e2e)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        _lib.stats_begin(with_events=with_events)
+        evs = []
+        with ClockSampler(local) as cs:
+            for _ in range(args.steps):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                frame(e2e)
+                if with_events and getattr(m.fused, "last_trace_stats", None) is not None:
+                    stats["evals"] += int(m.fused.last_trace_stats[1]); stats["rays"] += 1
+                e.record()
+                evs.append((s, e))
+            torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        calls, launches, times = _lib.stats_end()
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches, times, cs.summary()
+
+    ms_dev, launches, _, clocks = timed(False, False)
+    ms_e2e, _, _, _ = timed(True, False)
+    _, _, ktimes, _ = timed(False, True)               # per-kernel CUDA-event times (serialising events: outside the reported time)
+    hbm, peak_src = peaks()
+    roof = None
+    name = "psdf_sdf_sphere_trace"
+    if name in ktimes and stats["rays"]:
+        n, tot_ms = ktimes[name]
+        evals_per_launch = stats["evals"] / stats["rays"]
+        alg = 12 + 16 * 4 * 8                      # per network evaluation: position + 16 levels x 4 vertices x 8 B (SURVEY.md 8d, fused: no feature write)
+        ach = alg * evals_per_launch * n / (tot_ms / 1e3) / 1e9
+        top = sorted(((v[1], k) for k, v in ktimes.items()), reverse=True)
+        roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": ncu_traffic_from_profiles().get(name),
+                "launches": n, "avg_us": tot_ms / n * 1e3, "network_evaluations_per_launch": evals_per_launch, "peak_source": peak_src,
+                "share_of_step": tot_ms / n / (ms_dev / args.steps), "top5_ms_per_step": {k: round(v / args.steps, 4) for v, k in top[:5]}}
+    if rank == 0:
+        px = W * H * args.steps
+        out = {"metric": "sphere-trace px/sec (%dx%d, %d iterations max, occupancy grid on, normals + colour)" % (W, H, args.trace_iters),
+               "value": px / (ms_dev / 1e3), "unit": "px/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+               "data": "synthetic", "impl": "ours",
+               "config": {"workload": "C5: sphere-trace inference %dx%d, %d max steps, OccupancyGrid 256^3 on, 16-level lattice 2^18x2, 3x64 SDF MLP fitted "
+                                      "to the analytic sphere, RGB Lipschitz MLP; image tiled by rows over the ranks + one all_gather" % (W, H, args.trace_iters),
+                          "parallelism": "tiles%d" % world, "l2": "lattice table 33.5 MB + 16.8 MB occupancy are L2 resident by design; no flush",
+                          "timed_region": "sum of per-frame CUDA-event intervals"},
+               "e2e": {"value": px / (ms_e2e / 1e3), "unit": "px/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 24 * world,
+                       "d2h_bytes_per_step": W * H * 3 * 4},
+               "gpu_launches": launches, "clocks": clocks, "roofline": roof,
+               "cpu_baseline": cpu_baseline(sample_rays=8, steps=3, warmup=1)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+NCU_KERNEL_OF = {"psdf_sdf_fused_forward": "k_sdf_fused<1>", "psdf_sdf_fused_backward": "k_sdf_fused_backward",
+                 "psdf_rgb_fused_forward": "k_rgb_fused", "psdf_rgb_fused_backward": "k_rgb_fused_backward",
+                 "psdf_sdf_sphere_trace": "k_sdf_sphere_trace"}
+
+
+def ncu_traffic_from_profiles():
+    """entry point -> DRAM bytes (read + write) per launch, read from the newest tracked profiles/r*_ncu_kernels.csv (65 536-sample
+    launches of the bench workload). None for kernels the capture does not hold."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_kernels.csv")))
+    out = {}
+    if not files:
+        return out
+    rows = list(csv.DictReader(open(files[-1])))
+    for entry, kern in NCU_KERNEL_OF.items():
+        for r in rows:
+            if r.get("kernel", "").startswith(kern):
+                try:
+                    out[entry] = (float(r["dram__bytes_read.sum [Mbyte]"]) + float(r["dram__bytes_write.sum [Mbyte]"])) * 1e6
+                except (KeyError, ValueError):
+                    pass
+                break
     return out
 
 
@@ -320,10 +478,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python (no CUDA-graph replay)")
     ap.add_argument("--modular", action="store_true", help="drop-in API path only (encoding kernels + torch MLP), no fused tcgen05 kernels")
+    ap.add_argument("--rays", type=int, default=512, help="rays per GPU and step (512 = BASELINE config 2, 8192 = config 4 per GPU)")
+    ap.add_argument("--workload", default="train", choices=["train", "sphere_trace"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--trace_iters", type=int, default=256)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "sphere_trace":
+        run_sphere_trace(args)
     else:
         run_ours(args)
 

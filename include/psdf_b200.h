@@ -236,8 +236,9 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
  *   sdf = SDF(p); p += dir * sdf * sdf_multiplier; converged |= |sdf| < tresh | left the occupied region / bounding sphere
  * with advance_sample_to_next_occupied_voxel applied after every step when an occupancy grid is given (occupancy != NULL; else
  * the bounding-sphere test). Persistent CTAs of 128 ray slots pull rays from a global queue and refill finished slots;
- * pos [N,3] start points, dirs [N,3]; pos_out [N,3], converged [N] (may be NULL); queue_counter: device int32 [2], ZERO on entry:
- * [0] scratch (ray queue), [1] += number of network evaluations of the launch (statistics). Bit-identical per ray to the masked Python loop on the per-op kernels. */
+ * pos [N,3] start points, dirs [N,3]; pos_out [N,3], converged [N] (may be NULL); queue_counter: device int32 [8], ZERO on entry:
+ * [0] scratch (ray queue); statistics of the launch: [1] network evaluations, [2] rounds summed over the CTAs, [3] rounds that ran the
+ * network, [4] rounds of the longest CTA. Bit-identical per ray to the masked Python loop on the per-op kernels. */
 int psdf_sdf_sphere_trace(int N, int L, int T, const float* pos, const float* dirs, const float* lattice, const float* scale_factor,
                           const float* shift, const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob,
                           int nr_iters, float sdf_multiplier, float sdf_converged_tresh, const uint8_t* occupancy, int V, float extent,

@@ -107,6 +107,13 @@ def call(name, *args):
     import torch
     lib = load_library()
     ret, protos = PROTOS[name]
+    # launch on the device that holds the tensors (and on ITS current stream), not on whatever device happens to be current
+    for a in args:
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            if a.device.index != torch.cuda.current_device():
+                with torch.cuda.device(a.device):
+                    return call(name, *args)
+            break
     if len(args) == len(protos) - 1 and protos and protos[-1][0] == "stream":
         args = args + (torch.cuda.current_stream().cuda_stream,)
     if len(args) != len(protos):
@@ -162,15 +169,15 @@ _KERNELS_PER_CALL = {"psdf_packed_compact_scan": 2, "psdf_vr_combine_uniform_sam
 
 
 def _bwd_kernels(args):
-    """fused backward calls launch (reverse sweep, dW) once per chunk of one wave of 128-sample tiles (csrc/fused_*_bwd.cu)"""
-    import torch
+    """the colour-network backward launches (reverse sweep, dW) once per chunk of 128-sample tiles (csrc/fused_rgb_bwd.cu); the SDF
+    backward is a single kernel (weight gradients formed on chip, csrc/fused_sdf_bwd.cu)"""
     tiles = (int(args[0]) + 127) // 128
     chunk = int(os.environ.get("PSDF_BWD_CHUNK_TILES", "0"))
     chunk = tiles if chunk <= 0 else chunk
     return 2 * max(1, (tiles + chunk - 1) // chunk)
 
 
-_KERNELS_FN = {"psdf_sdf_fused_backward": _bwd_kernels, "psdf_rgb_fused_backward": _bwd_kernels}
+_KERNELS_FN = {"psdf_rgb_fused_backward": _bwd_kernels}
 _STATS = None
 LAST_UNITS = {}        # {entry point: sum of its leading count argument} of the last stats window
 

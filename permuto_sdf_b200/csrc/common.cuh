@@ -234,6 +234,52 @@ __device__ __forceinline__ bool occ_advance_to_next_occupied(const GridGeom& g, 
     }
     return true;
 }
+// The same march as occ_advance_to_next_occupied, resumable: at most `max_batches` batches of 8 steps per call, the march state (t, steps)
+// lives with the caller. Returns 0: still marching (call again with the same origin), 1: stopped inside the grid (occupied voxel
+// reached, or step budget exhausted: position unchanged), 2: left the grid. On 1 / 2 the position is written like the one-shot version.
+// Decisions are taken in the same order on the same values, so the result is bit-identical however the batches are cut.
+__device__ __forceinline__ int occ_advance_resumable(const GridGeom& g, const uint8_t* __restrict__ occ, float& ox, float& oy, float& oz,
+                                                     float dx, float dy, float dz, float& t, int& steps, int max_batches) {
+    const int nv = g.V * g.V * g.V;
+    const float eps = 1e-6f;
+    const float ix = safe_inv(dx), iy = safe_inv(dy), iz = safe_inv(dz);
+    const double max_steps = (double)g.V * sqrt(3.0);
+    constexpr int kAhead = 8;
+    for (int b = 0; b < max_batches; b++) {
+        if (!((double)steps < max_steps)) return 1;
+        float bx[kAhead], by[kAhead], bz[kAhead];
+        int bv[kAhead];
+        int m = 0;
+        bool oob_at_m = false;
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) {
+            if (!oob_at_m && (double)(steps + k) < max_steps) {
+                const float px = __fmaf_rn(dx, t, ox), py = __fmaf_rn(dy, t, oy), pz = __fmaf_rn(dz, t, oz);
+                const int v = pos_to_voxel(px, py, pz, g);
+                bx[k] = px; by[k] = py; bz[k] = pz; bv[k] = v;
+                m = k + 1;
+                if (v > (nv - 1) || v < 0) oob_at_m = true;
+                else {
+                    const float dn = dda_step(px, py, pz, dx, dy, dz, ix, iy, iz, g.V);
+                    t = __fadd_rn(__fadd_rn(t, dn), eps);
+                }
+            }
+        }
+        uint8_t bo[kAhead];
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) bo[k] = (k < m && !(oob_at_m && k == m - 1)) ? __ldg(occ + bv[k]) : 0;
+#pragma unroll
+        for (int k = 0; k < kAhead; k++) {
+            if (k < m) {
+                if (oob_at_m && k == m - 1) { ox = bx[k]; oy = by[k]; oz = bz[k]; return 2; }
+                if (bo[k]) { ox = bx[k]; oy = by[k]; oz = bz[k]; return 1; }
+            }
+        }
+        if (m == 0) return 1;
+        steps += m;
+    }
+    return ((double)steps < max_steps) ? 0 : 1;
+}
 inline GridGeom make_grid_geom(int V, float extent, const float* t) {
     GridGeom g;
     g.V = V; g.extent = extent; g.tx = t[0]; g.ty = t[1]; g.tz = t[2];

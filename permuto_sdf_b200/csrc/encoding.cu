@@ -31,7 +31,7 @@ struct EncParams {
     int N, L, T, C;          // samples, levels, table capacity, output columns
     int concat;              // concat raw points
     float points_scaling;
-    unsigned cap_mask;       // T-1 when T is a power of two, else 0
+    unsigned cap_mask;       // floor(2^32 / T): multiplier of the division-free h mod T (see vertex_index)
 };
 
 template <int D>
@@ -126,7 +126,9 @@ __device__ __forceinline__ unsigned vertex_index(const Simplex<D>& s, int r, con
         h += (unsigned)key;
         h *= 2531011u;
     }
-    return p.cap_mask ? (h & p.cap_mask) : (h % (unsigned)p.T);
+    // h mod T without a division: umulhi(h, floor(2^32 / T)) is the quotient or one less -> one conditional subtraction
+    const unsigned rem = h - __umulhi(h, p.cap_mask) * (unsigned)p.T;
+    return rem >= (unsigned)p.T ? rem - (unsigned)p.T : rem;
 }
 
 // reverse of locate()'s weight scatter + elevation: dL/dbary[0..D] -> dL/dx (before the per-dim scale)
@@ -456,7 +458,7 @@ inline int make_params(EncParams& p, int N, int D, int L, int F, int T, int conc
     p.C = (L + E) * F;
     p.concat = concat;
     p.points_scaling = points_scaling;
-    p.cap_mask = ((T & (T - 1)) == 0) ? (unsigned)(T - 1) : 0u;
+    p.cap_mask = T <= 1 ? 0xffffffffu : (unsigned)(0x100000000ull / (unsigned long long)(unsigned)T);
     return PSDF_OK;
 }
 #define ST ((cudaStream_t)stream)

@@ -134,7 +134,10 @@ __device__ __forceinline__ void bary_tangent3(const float* dcf, const Simplex3& 
     by_rank(s, de, dD);
     db[0] = dD[3] - dD[0]; db[1] = dD[2] - dD[3]; db[2] = dD[1] - dD[2]; db[3] = dD[0] - dD[1];
 }
-__device__ __forceinline__ unsigned vindex3(const Simplex3& s, int r, unsigned cap_mask, unsigned T) {
+// h mod T without a division: q = umulhi(h, floor(2^32 / T)) is the quotient or one less, so one conditional subtraction finishes it
+// (exact for every 32-bit h; a power-of-two T needs no correction). `magic` = t_magic(T), computed on the host.
+inline unsigned t_magic(int T) { return T <= 1 ? 0xffffffffu : (unsigned)(0x100000000ull / (unsigned long long)(unsigned)T); }
+__device__ __forceinline__ unsigned vindex3(const Simplex3& s, int r, unsigned magic, unsigned T) {
     unsigned h = 0;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -143,7 +146,8 @@ __device__ __forceinline__ unsigned vindex3(const Simplex3& s, int r, unsigned c
         h += (unsigned)key;
         h *= 2531011u;
     }
-    return cap_mask ? (h & cap_mask) : (h % T);
+    unsigned rem = h - __umulhi(h, magic) * T;
+    return rem >= T ? rem - T : rem;
 }
 
 // exact (erf) GELU and derivatives from one exp and one reciprocal: Phi(z) by Abramowitz-Stegun 7.1.26 (|err| < 1e-7),
@@ -163,7 +167,7 @@ __device__ __forceinline__ GeluEval gelu_eval(float z) {
 
 struct FusedParams {
     int N, L, T;
-    unsigned cap_mask;
+    unsigned cap_mask;   // t_magic(T): multiplier of the division-free h mod T (any capacity, not only powers of two)
     float points_scaling;
     int in_dim;          // (L + E) * 2 feature columns
     MlpGeom g;
@@ -248,6 +252,9 @@ __device__ __forceinline__ float2 add_peers2(unsigned peers, float2 x, int lane)
 }
 __device__ __forceinline__ void red_v2(float* addr, float2 v) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void red_v4(float* addr, float a, float b, float c, float d) {     // 16-byte aligned address
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 // column sums of 16 per-lane values over the 32 lanes of a warp with 16 shuffles (halving butterfly): afterwards both
 // lanes of the pair {2p, 2p+1} hold the sum of column `col` = bit-reversal-free index built from lane bits 4..1.

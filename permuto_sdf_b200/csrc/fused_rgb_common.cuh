@@ -33,7 +33,7 @@ struct RgbParams {
 inline int make_rgb_params(RgbParams& P, int N, int L, int T, int geom_dim, float points_scaling, int h1, int h2, int h3) {
     if (N < 0 || L < 4 || L > kMaxLevels || (L % 4) != 0 || geom_dim != kGeomDim) return -3;
     P.N = N; P.L = L; P.T = T;
-    P.cap_mask = ((T & (T - 1)) == 0) ? (unsigned)(T - 1) : 0u;
+    P.cap_mask = t_magic(T);
     P.points_scaling = points_scaling;
     P.enc_cols = 2 * L + 4;
     P.in_dim = P.enc_cols + kShCols + 3 + kGeomDim;
@@ -81,6 +81,29 @@ __device__ __forceinline__ void issue_gemm_w(uint32_t tmem_d, const uint8_t* a_h
         umma::mma_bf16(tmem_d, dah0 + off, dwh0 + off, idesc, kk > 0 ? 1u : 0u);
         umma::mma_bf16(tmem_d, dah0 + off, dwl0 + off, idesc, 1u);
         umma::mma_bf16(tmem_d, dal0 + off, dwh0 + off, idesc, 1u);
+    }
+}
+
+// The MMA sequence of a layer is issued by four threads (lane 0 of warps 0..3, one per SM sub-partition), each owning a quarter of the
+// accumulator columns (in units of 16): the single-thread issue latency shrinks four-fold; all four commit to the layer's mbarrier.
+__device__ __forceinline__ void split4(int N, int part, int& n0, int& nn) {
+    const int u = N / 16, base = u / 4, rem = u % 4;
+    n0 = (part * base + (part < rem ? part : rem)) * 16;
+    nn = (base + (part < rem ? 1 : 0)) * 16;
+}
+__device__ __forceinline__ void issue_gemm_w_part(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
+                                                  const uint8_t* w_lo, int Kp, int n0, int nn) {
+    if (nn <= 0) return;
+    const uint32_t idesc = umma::make_idesc(128, nn, umma::kFmtBF16);
+    const uint32_t sbo_w = (Kp / 8) * kLBO;
+    const uint32_t woff = (n0 / 8) * sbo_w;
+    const uint64_t dah0 = umma::make_desc(umma::smem_u32(a_hi), kLBO, kWSBO), dal0 = umma::make_desc(umma::smem_u32(a_lo), kLBO, kWSBO);
+    const uint64_t dwh0 = umma::make_desc(umma::smem_u32(w_hi) + woff, kLBO, sbo_w), dwl0 = umma::make_desc(umma::smem_u32(w_lo) + woff, kLBO, sbo_w);
+    for (int kk = 0; kk < Kp / 16; kk++) {
+        const uint64_t off = (uint64_t)(kk * ((2 * kLBO) >> 4));
+        umma::mma_bf16(tmem_d + n0, dah0 + off, dwh0 + off, idesc, kk > 0 ? 1u : 0u);
+        umma::mma_bf16(tmem_d + n0, dah0 + off, dwl0 + off, idesc, 1u);
+        umma::mma_bf16(tmem_d + n0, dal0 + off, dwh0 + off, idesc, 1u);
     }
 }
 

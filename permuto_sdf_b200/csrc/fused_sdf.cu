@@ -47,7 +47,7 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
 
     if (tid == 0) {
         umma::mbar_init(&bars[0], 1);
-        umma::mbar_init(&bars[1], 1);
+        umma::mbar_init(&bars[1], S);          // one tcgen05.commit per issuing thread (one per stream)
         umma::mbar_fence_init();
     }
     for (int i = tid; i < P.L * 3; i += kFusedThreads) {
@@ -150,11 +150,13 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
             umma::fence_async_smem();
             umma::fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
+            if ((tid & 31) == 0 && warp < S) {
+                // stream s is issued by lane 0 of warp s: the four single-thread issue sequences run on four different SM
+                // sub-partitions side by side; the mbarrier completes when all S commits have arrived
+                const int s = warp;
                 umma::fence_after_sync();
-                for (int s = 0; s < S; s++)
-                    issue_gemm(tmem_base + s * 64, s_a + s * 2 * kATileBytes, s_a + s * 2 * kATileBytes + kATileBytes, s_blob + P.g.w_hi[l],
-                               s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
+                issue_gemm(tmem_base + s * 64, s_a + s * 2 * kATileBytes, s_a + s * 2 * kATileBytes + kATileBytes, s_blob + P.g.w_hi[l],
+                           s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
                 umma::commit(&bars[1]);
             }
             umma::mbar_wait(&bars[1], mma_phase);
@@ -249,7 +251,10 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
     float* s_dir = s_pos + kTile * 3;                      // [128][3]
     int* s_ray = reinterpret_cast<int*>(s_dir + kTile * 3);   // [128] ray index of the slot, -1: empty
     int* s_it = s_ray + kTile;                             // [128] evaluations done for the slot's ray
-    int* s_flag = s_it + kTile;                            // [0]: queue drained
+    int* s_ms = s_it + kTile;                              // [128] DDA steps of a march in progress, -1: not marching
+    float* s_mt = reinterpret_cast<float*>(s_ms + kTile);  // [128] march parameter t of a march in progress
+    int* s_new = reinterpret_cast<int*>(s_mt + kTile);     // [128] |sdf| < threshold at the evaluation that started the march
+    int* s_flag = s_new + kTile;                           // [0]: queue drained
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_flag + 2);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -277,6 +282,7 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
         }
         s_ray[row] = ok ? n : -1;
         s_it[row] = 0;
+        s_ms[row] = -1;
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -288,14 +294,23 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
     const float* bias3 = reinterpret_cast<const float*>(s_blob + P.g.bias[kNL - 1]);
     const int first_queued = gridDim.x * kTile;
 
+    // A long empty-space march (hundreds of dependent DDA steps, ~25 us) must not stall the other 127 slots: the march after a step is
+    // cut into rounds of kMarchBatches x 8 DDA steps; a slot whose march is not finished keeps its state (s_mt, s_ms) and sits out the
+    // network evaluations until it is (occ_advance_resumable: same decisions in the same order, so the result does not change).
+    constexpr int kMarchBatches = 8;
     int evaluations = 0;                                      // network evaluations of this CTA (same value in every thread)
+    int rounds = 0, net_rounds = 0;
     while (true) {
-        const bool active = s_ray[row] >= 0;
+        const bool occupied = s_ray[row] >= 0;
+        const bool active = occupied && s_ms[row] < 0;       // evaluates the network in this round
+        if (__syncthreads_count(occupied) == 0) break;       // no ray left in this tile (and the queue is drained)
         const int nact = __syncthreads_count(active);
-        if (nact == 0) break;                                // no ray left in this tile (and the queue is drained)
         evaluations += nact / kGroups;
         float x[3] = {s_pos[row * 3], s_pos[row * 3 + 1], s_pos[row * 3 + 2]};
-        if (active && Q.nr_iters > 0) {
+        const bool run_net = nact > 0 && Q.nr_iters > 0;      // uniform
+        rounds++;
+        net_rounds += run_net ? 1 : 0;
+        if (active && run_net) {
             for (int kc = grp; kc < all_cores; kc += kGroups) {
                 float fv[8];
                 if (kc < level_cores) {
@@ -332,60 +347,79 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
                 store8(s_a, s_a + kATileBytes, row, kc, fv);
             }
         }
+        float sdf = 0.f;
+        if (run_net) {
 #pragma unroll 1
-        for (int l = 0; l < kNL; l++) {
-            umma::fence_async_smem();
-            umma::fence_before_sync();
-            __syncthreads();
-            if (tid == 0) {
-                umma::fence_after_sync();
-                issue_gemm(tmem_base, s_a, s_a + kATileBytes, s_blob + P.g.w_hi[l], s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
-                umma::commit(&bars[1]);
-            }
-            umma::mbar_wait(&bars[1], mma_phase);
-            mma_phase ^= 1;
-            umma::fence_after_sync();
-            const float* bias = reinterpret_cast<const float*>(s_blob + P.g.bias[l]);
-            const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-            const int c = grp;
-            if (l < kNL - 1) {
-                if (c < P.g.Np[l] / 16) {
-                    float z[16];
-                    umma::tmem_ld16(trow + c * 16, z);
-                    umma::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; i++) { const float zz = z[i] + bias[c * 16 + i]; z[i] = zz * gelu_eval(zz).cdf; }
-                    store8(s_a, s_a + kATileBytes, row, 2 * c, z);
-                    store8(s_a, s_a + kATileBytes, row, 2 * c + 1, z + 8);
+            for (int l = 0; l < kNL; l++) {
+                umma::fence_async_smem();
+                umma::fence_before_sync();
+                __syncthreads();
+                if (tid == 0) {
+                    umma::fence_after_sync();
+                    issue_gemm(tmem_base, s_a, s_a + kATileBytes, s_blob + P.g.w_hi[l], s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
+                    umma::commit(&bars[1]);
                 }
-            } else if (grp == 0) {
-                float z[16];
-                umma::tmem_ld16(trow, z);
-                umma::tmem_ld_wait();
-                bool need = !active && s_flag[0] == 0;         // empty slot: try the queue again unless it is known to be drained
-                if (active) {
-                    const int ray = s_ray[row];
-                    float px = x[0], py = x[1], pz = x[2];
-                    bool done = true, conv = false;
-                    if (Q.nr_iters > 0) {
-                        const float sdf = z[0] + bias3[0];
-                        const float dx = s_dir[row * 3], dy = s_dir[row * 3 + 1], dz = s_dir[row * 3 + 2];
+                umma::mbar_wait(&bars[1], mma_phase);
+                mma_phase ^= 1;
+                umma::fence_after_sync();
+                const float* bias = reinterpret_cast<const float*>(s_blob + P.g.bias[l]);
+                const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+                const int c = grp;
+                if (l < kNL - 1) {
+                    if (c < P.g.Np[l] / 16) {
+                        float z[16];
+                        umma::tmem_ld16(trow + c * 16, z);
+                        umma::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i++) { const float zz = z[i] + bias[c * 16 + i]; z[i] = zz * gelu_eval(zz).cdf; }
+                        store8(s_a, s_a + kATileBytes, row, 2 * c, z);
+                        store8(s_a, s_a + kATileBytes, row, 2 * c + 1, z + 8);
+                    }
+                } else if (grp == 0) {
+                    float z[16];
+                    umma::tmem_ld16(trow, z);
+                    umma::tmem_ld_wait();
+                    sdf = z[0] + bias3[0];
+                }
+                umma::fence_before_sync();
+            }
+        }
+        // ---- step / march / refill: one thread per slot
+        if (grp == 0) {
+            bool need = !occupied && s_flag[0] == 0;           // empty slot: try the queue again unless it is known to be drained
+            if (occupied) {
+                const int ray = s_ray[row];
+                const float dx = s_dir[row * 3], dy = s_dir[row * 3 + 1], dz = s_dir[row * 3 + 2];
+                float px = x[0], py = x[1], pz = x[2];
+                bool finished = true, conv = false, newly = false, within = true;
+                float t = 0.f;
+                int steps = 0;
+                if (Q.nr_iters > 0) {
+                    if (active) {                              // this round's evaluation: step along the ray
                         px = __fadd_rn(x[0], __fmul_rn(__fmul_rn(dx, sdf), Q.sdf_mult));
                         py = __fadd_rn(x[1], __fmul_rn(__fmul_rn(dy, sdf), Q.sdf_mult));
                         pz = __fadd_rn(x[2], __fmul_rn(__fmul_rn(dz, sdf), Q.sdf_mult));
-                        const bool newly = fabsf(sdf) < Q.conv_thresh;
-                        bool within;
-                        if (Q.has_occ) within = psdf::occ_advance_to_next_occupied(Q.grid, occ, px, py, pz, dx, dy, dz);
-                        else {
-                            const float qx = __fsub_rn(px, Q.sph_cx), qy = __fsub_rn(py, Q.sph_cy), qz = __fsub_rn(pz, Q.sph_cz);
-                            within = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz))) < Q.sph_radius;
-                        }
-                        conv = newly || !within;
-                        const int it = s_it[row] + 1;
-                        s_it[row] = it;
-                        done = conv || it >= Q.nr_iters;
+                        newly = fabsf(sdf) < Q.conv_thresh;
+                        s_it[row] = s_it[row] + 1;
+                    } else {                                   // march in progress: origin = s_pos, state from the previous round
+                        t = s_mt[row]; steps = s_ms[row]; newly = s_new[row] != 0;
                     }
-                    if (done) {
+                    if (Q.has_occ) {
+                        const int st = psdf::occ_advance_resumable(Q.grid, occ, px, py, pz, dx, dy, dz, t, steps, kMarchBatches);
+                        if (st == 0) {                         // not there yet: keep the march origin and state, sit out the next evaluation
+                            finished = false;
+                            if (active) { s_pos[row * 3] = px; s_pos[row * 3 + 1] = py; s_pos[row * 3 + 2] = pz; }
+                            s_mt[row] = t; s_ms[row] = steps; s_new[row] = newly ? 1 : 0;
+                        } else within = (st == 1);
+                    } else {
+                        const float qx = __fsub_rn(px, Q.sph_cx), qy = __fsub_rn(py, Q.sph_cy), qz = __fsub_rn(pz, Q.sph_cz);
+                        within = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(qx, qx), __fmul_rn(qy, qy)), __fmul_rn(qz, qz))) < Q.sph_radius;
+                    }
+                    if (finished) conv = newly || !within;
+                }
+                if (finished) {
+                    s_ms[row] = -1;
+                    if (conv || s_it[row] >= Q.nr_iters) {     // the ray is done: result out, slot free
                         pos_out[(size_t)ray * 3] = px; pos_out[(size_t)ray * 3 + 1] = py; pos_out[(size_t)ray * 3 + 2] = pz;
                         if (converged_out) converged_out[ray] = (uint8_t)conv;
                         need = true;
@@ -393,35 +427,40 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
                         s_pos[row * 3] = px; s_pos[row * 3 + 1] = py; s_pos[row * 3 + 2] = pz;
                     }
                 }
-                // refill: one atomicAdd per warp for all its free slots
-                const unsigned want = __ballot_sync(0xffffffffu, need);
-                if (want) {
-                    int base = 0;
-                    if (lane == __ffs(want) - 1) base = atomicAdd(queue, __popc(want));
-                    base = __shfl_sync(0xffffffffu, base, __ffs(want) - 1);
-                    if (need) {
-                        const int nr = first_queued + base + __popc(want & ((1u << lane) - 1u));
-                        if (nr < P.N) {
+            }
+            // refill: one atomicAdd per warp for all its free slots
+            const unsigned want = __ballot_sync(0xffffffffu, need);
+            if (want) {
+                int base = 0;
+                if (lane == __ffs(want) - 1) base = atomicAdd(queue, __popc(want));
+                base = __shfl_sync(0xffffffffu, base, __ffs(want) - 1);
+                if (need) {
+                    const int nr = first_queued + base + __popc(want & ((1u << lane) - 1u));
+                    if (nr < P.N) {
 #pragma unroll
-                            for (int i = 0; i < 3; i++) {
-                                s_pos[row * 3 + i] = pos_in[(size_t)nr * 3 + i];
-                                s_dir[row * 3 + i] = dirs[(size_t)nr * 3 + i];
-                            }
-                            s_ray[row] = nr;
-                            s_it[row] = 0;
-                        } else {
-                            s_ray[row] = -1;
-                            s_flag[0] = 1;
+                        for (int i = 0; i < 3; i++) {
+                            s_pos[row * 3 + i] = pos_in[(size_t)nr * 3 + i];
+                            s_dir[row * 3 + i] = dirs[(size_t)nr * 3 + i];
                         }
+                        s_ray[row] = nr;
+                        s_it[row] = 0;
+                        s_ms[row] = -1;
+                    } else {
+                        s_ray[row] = -1;
+                        s_flag[0] = 1;
                     }
                 }
             }
-            umma::fence_before_sync();
         }
-        __syncthreads();      // slots of this iteration visible, TMEM reads done
+        __syncthreads();      // slots of this round visible, TMEM reads done
     }
     __syncthreads();
-    if (tid == 0 && evaluations) atomicAdd(queue + 1, evaluations);     // statistics: total network evaluations of the launch
+    if (tid == 0 && evaluations) {      // statistics of the launch: network evaluations, rounds, rounds that ran the network, longest CTA
+        atomicAdd(queue + 1, evaluations);
+        atomicAdd(queue + 2, rounds);
+        atomicAdd(queue + 3, net_rounds);
+        atomicMax(queue + 4, rounds);
+    }
     if (warp == 0) umma::tmem_dealloc(tmem_base, 64);
 }
 
@@ -570,7 +609,7 @@ int psdf_sdf_sphere_trace(int N, int L, int T, const float* pos, const float* di
     if (N == 0) return PSDF_OK;
     FusedParams P;
     P.N = N; P.L = L; P.T = T;
-    P.cap_mask = ((T & (T - 1)) == 0) ? (unsigned)(T - 1) : 0u;
+    P.cap_mask = t_magic(T);
     P.points_scaling = points_scaling;
     P.in_dim = (L + 2) * 2;
     if (P.in_dim > 64) return PSDF_ERR_UNSUPPORTED;
@@ -584,7 +623,7 @@ int psdf_sdf_sphere_trace(int N, int L, int T, const float* pos, const float* di
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + kTile * 8 * sizeof(float) + 96;
+    const size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + kTile * 11 * sizeof(float) + 96;
     cudaFuncSetAttribute(k_sdf_sphere_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     const int ntiles = div_up(N, kTile);
     k_sdf_sphere_trace<<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, Q, pos, dirs, reinterpret_cast<const float2*>(lattice), scale_factor,
@@ -624,7 +663,7 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
     if (N == 0) return PSDF_OK;
     FusedParams P;
     P.N = N; P.L = L; P.T = T;
-    P.cap_mask = ((T & (T - 1)) == 0) ? (unsigned)(T - 1) : 0u;
+    P.cap_mask = t_magic(T);
     P.points_scaling = points_scaling;
     P.in_dim = (L + 2) * 2;                       // D = 3, F = 2: E = 2 concat levels
     if (P.in_dim > 64) return PSDF_ERR_UNSUPPORTED;
@@ -636,13 +675,11 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
     const float2* lat = reinterpret_cast<const float2*>(lattice);
     if (grad) {
         size_t smem = (size_t)P.g.total + 4 * 2 * kATileBytes + sizeof(LevelC) + 64;
-        static bool attr_done = false;
-        if (!attr_done) { cudaFuncSetAttribute(k_sdf_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_done = true; }
+        cudaFuncSetAttribute(k_sdf_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      // per device: set on every call (a second GPU needs its own opt-in)
         k_sdf_fused<true><<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
     } else {
         size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + 64;
-        static bool attr_done = false;
-        if (!attr_done) { cudaFuncSetAttribute(k_sdf_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024); attr_done = true; }
+        cudaFuncSetAttribute(k_sdf_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);      // per device: set on every call (a second GPU needs its own opt-in)
         k_sdf_fused<false><<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
     }
     PSDF_CHECK_LAUNCH();

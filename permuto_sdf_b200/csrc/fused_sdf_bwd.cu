@@ -33,6 +33,8 @@
 //      second accumulator lives at lane offset 16 of the same columns (validated on B200: tests/test_umma_probe_gpu.py).
 //   5. encoder backward: warp-aggregated red.global.add.v2.f32 into the lattice gradient.
 // TMEM map (512 columns): [0,256) z_1 | tz_1 | z_2 | tz_2, [256,384) work (value | tangent), [384,512) dW_0/dW_1, dW_2/dW_3.
+#include <cstdio>
+#include <cstdlib>
 #include "fused_common.cuh"
 #include "../../include/psdf_b200.h"
 
@@ -48,7 +50,19 @@ struct BwdOut {
     uint8_t* a0_spill;  // [ntiles][64 KB] encoder operand tiles, written and re-read by the same CTA
     float* gW[kNL];     // [N_l, K_l] (+=)
     float* gbias[kNL];  // [N_l]      (+=)
+    unsigned long long* phase_cycles;   // [16] += clock64 deltas of thread 0 per phase (PSDF_PHASE_TIMING=1, diagnostics), else NULL
 };
+// phase ids of the diagnostic counters
+enum { kPhEncoder = 0, kPhForward = 1, kPhSeed = 2, kPhReverse3 = 3, kPhReverse2 = 4, kPhReverse1 = 5, kPhReverse0 = 6, kPhEncoderBwd = 7,
+       kPhFlush = 8, kPhTiles = 9 };
+#define PSDF_PHASE(id)                                                                     \
+    do {                                                                                   \
+        if (out.phase_cycles && tid == 0) {                                                \
+            const long long now_ = clock64();                                              \
+            atomicAdd(out.phase_cycles + (id), (unsigned long long)(now_ - phase_t0));     \
+            phase_t0 = now_;                                                               \
+        }                                                                                  \
+    } while (0)
 
 // in place for 16 accumulator columns (zz = z + bias): z <- a = gelu(zz), tz <- ta = gelu'(zz) tz; g1 = gelu'(zz), g2t = gelu''(zz) tz
 __device__ __forceinline__ void activations16(float* z, float* tz, const float* bias, float* g1, float* g2t) {
@@ -70,38 +84,64 @@ __device__ __forceinline__ void store_set16(uint8_t* set, int row, int c, const 
     store8(set + 2 * kATileBytes, set + 3 * kATileBytes, row, 2 * c + 1, ta + 8);
 }
 
-// abar = zbar W for both streams (single thread): A = zbar tile set [128 x Np] K-major, B = forward weight tile [Np rows][Kp] read as an
-// MN-major operand (reduction over the rows: 8-row groups are sbo_w apart, the k cores kLBO), result Kp columns at tmem_d (+64: tangent)
-__device__ __forceinline__ void issue_reverse(uint32_t tmem_d, const uint8_t* zset, const uint8_t* w_hi, const uint8_t* w_lo, int Kp, int Np) {
-    const uint32_t idesc = umma::make_idesc(128, Kp, umma::kFmtBF16) | (1u << 16);
+// The tcgen05.mma sequences of a phase are issued by several threads (lane 0 of warps 0..3 for the forward / reverse GEMMs, of warps
+// 4..5 for the weight gradients): each issuer owns a disjoint slice of the accumulator columns (stream x half of N), so the
+// single-thread issue latency is divided by the number of issuers and runs on different SM sub-partitions; every issuer commits
+// to the phase's mbarrier (initialised with the issuer count).
+__device__ __forceinline__ void split_n(int N, int half, int& n0, int& nn) {      // halves in units of 16 columns (MMA N % 16 == 0)
+    const int na = ((N / 16 + 1) / 2) * 16;
+    n0 = half ? na : 0;
+    nn = half ? N - na : na;
+}
+// columns [n0, n0 + nn) of one stream of  D[128 x Np] = A[128 x Kp] W^T  (A, W K-major)
+__device__ __forceinline__ void issue_forward_part(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
+                                                   const uint8_t* w_lo, int Kp, int n0, int nn) {
+    if (nn <= 0) return;
+    const uint32_t idesc = umma::make_idesc(128, nn, umma::kFmtBF16);
     const uint32_t sbo_w = (Kp / 8) * kLBO;
-    const uint64_t dwh0 = umma::make_desc(umma::smem_u32(w_hi), sbo_w, kLBO), dwl0 = umma::make_desc(umma::smem_u32(w_lo), sbo_w, kLBO);
-#pragma unroll 1
-    for (int s = 1; s >= 0; s--) {                       // tangent stream first: its result is consumed first
-        const uint64_t dzh0 = umma::make_desc(umma::smem_u32(zset + s * 2 * kATileBytes), kLBO, kSBO_A);
-        const uint64_t dzl0 = umma::make_desc(umma::smem_u32(zset + s * 2 * kATileBytes + kATileBytes), kLBO, kSBO_A);
-        for (int kk = 0; kk < Np / 16; kk++) {
-            const uint64_t oa = (uint64_t)(kk * ((2 * kLBO) >> 4)), ow = (uint64_t)(kk * ((2 * sbo_w) >> 4));
-            umma::mma_bf16(tmem_d + s * 64, dzh0 + oa, dwh0 + ow, idesc, kk > 0 ? 1u : 0u);
-            umma::mma_bf16(tmem_d + s * 64, dzh0 + oa, dwl0 + ow, idesc, 1u);
-            umma::mma_bf16(tmem_d + s * 64, dzl0 + oa, dwh0 + ow, idesc, 1u);
-        }
+    const uint32_t woff = (n0 / 8) * sbo_w;
+    const uint64_t dah0 = umma::make_desc(umma::smem_u32(a_hi), kLBO, kSBO_A), dal0 = umma::make_desc(umma::smem_u32(a_lo), kLBO, kSBO_A);
+    const uint64_t dwh0 = umma::make_desc(umma::smem_u32(w_hi) + woff, kLBO, sbo_w), dwl0 = umma::make_desc(umma::smem_u32(w_lo) + woff, kLBO, sbo_w);
+    for (int kk = 0; kk < Kp / 16; kk++) {
+        const uint64_t off = (uint64_t)(kk * ((2 * kLBO) >> 4));
+        umma::mma_bf16(tmem_d + n0, dah0 + off, dwh0 + off, idesc, kk > 0 ? 1u : 0u);
+        umma::mma_bf16(tmem_d + n0, dah0 + off, dwl0 + off, idesc, 1u);
+        umma::mma_bf16(tmem_d + n0, dal0 + off, dwh0 + off, idesc, 1u);
     }
 }
-// dW (+)= zbar^T a + tzbar^T ta: both tile sets consumed as MN-major operands, K = the 128 samples, M = 64 accumulator rows
-__device__ __forceinline__ void issue_dw(uint32_t tmem_d, const uint8_t* zset, const uint8_t* aset, int Kp, bool clear) {
-    const uint32_t idesc = umma::make_idesc_mn(64, Kp, umma::kFmtBF16);
+// columns [n0, n0 + nn) of one stream of  abar[128 x Kp] = zbar[128 x Np] W : A = zbar tiles K-major, B = the FORWARD weight tile
+// [Np rows][Kp] read as an MN-major operand (reduction over the rows: 8-row groups are sbo_w apart, the k cores kLBO)
+__device__ __forceinline__ void issue_reverse_part(uint32_t tmem_d, const uint8_t* z_hi, const uint8_t* z_lo, const uint8_t* w_hi,
+                                                   const uint8_t* w_lo, int Kp, int Np, int n0, int nn) {
+    if (nn <= 0) return;
+    const uint32_t idesc = umma::make_idesc(128, nn, umma::kFmtBF16) | (1u << 16);
+    const uint32_t sbo_w = (Kp / 8) * kLBO;
+    const uint32_t woff = (n0 / 8) * kLBO;
+    const uint64_t dwh0 = umma::make_desc(umma::smem_u32(w_hi) + woff, sbo_w, kLBO), dwl0 = umma::make_desc(umma::smem_u32(w_lo) + woff, sbo_w, kLBO);
+    const uint64_t dzh0 = umma::make_desc(umma::smem_u32(z_hi), kLBO, kSBO_A), dzl0 = umma::make_desc(umma::smem_u32(z_lo), kLBO, kSBO_A);
+    for (int kk = 0; kk < Np / 16; kk++) {
+        const uint64_t oa = (uint64_t)(kk * ((2 * kLBO) >> 4)), ow = (uint64_t)(kk * ((2 * sbo_w) >> 4));
+        umma::mma_bf16(tmem_d + n0, dzh0 + oa, dwh0 + ow, idesc, kk > 0 ? 1u : 0u);
+        umma::mma_bf16(tmem_d + n0, dzh0 + oa, dwl0 + ow, idesc, 1u);
+        umma::mma_bf16(tmem_d + n0, dzl0 + oa, dwh0 + ow, idesc, 1u);
+    }
+}
+// columns [n0, n0 + nn) of  dW (+)= zbar^T a + tzbar^T ta : both tile sets consumed as MN-major operands, K = the 128 samples, M = 64
+__device__ __forceinline__ void issue_dw_part(uint32_t tmem_d, const uint8_t* zset, const uint8_t* aset, int n0, int nn, bool clear) {
+    if (nn <= 0) return;
+    const uint32_t idesc = umma::make_idesc_mn(64, nn, umma::kFmtBF16);
+    const uint32_t aoff = (n0 / 8) * kLBO;
 #pragma unroll 1
     for (int s = 0; s < 2; s++) {
         const uint64_t dzh0 = umma::make_desc(umma::smem_u32(zset + s * 2 * kATileBytes), kSBO_A, kLBO);
         const uint64_t dzl0 = umma::make_desc(umma::smem_u32(zset + s * 2 * kATileBytes + kATileBytes), kSBO_A, kLBO);
-        const uint64_t dah0 = umma::make_desc(umma::smem_u32(aset + s * 2 * kATileBytes), kSBO_A, kLBO);
-        const uint64_t dal0 = umma::make_desc(umma::smem_u32(aset + s * 2 * kATileBytes + kATileBytes), kSBO_A, kLBO);
+        const uint64_t dah0 = umma::make_desc(umma::smem_u32(aset + s * 2 * kATileBytes) + aoff, kSBO_A, kLBO);
+        const uint64_t dal0 = umma::make_desc(umma::smem_u32(aset + s * 2 * kATileBytes + kATileBytes) + aoff, kSBO_A, kLBO);
         for (int kk = 0; kk < kTile / 16; kk++) {
             const uint64_t o = (uint64_t)(kk * ((2 * kSBO_A) >> 4));          // 16 samples = two 8-sample groups
-            umma::mma_bf16(tmem_d, dzh0 + o, dah0 + o, idesc, (clear && s == 0 && kk == 0) ? 0u : 1u);
-            umma::mma_bf16(tmem_d, dzh0 + o, dal0 + o, idesc, 1u);
-            umma::mma_bf16(tmem_d, dzl0 + o, dah0 + o, idesc, 1u);
+            umma::mma_bf16(tmem_d + n0, dzh0 + o, dah0 + o, idesc, (clear && s == 0 && kk == 0) ? 0u : 1u);
+            umma::mma_bf16(tmem_d + n0, dzh0 + o, dal0 + o, idesc, 1u);
+            umma::mma_bf16(tmem_d + n0, dzl0 + o, dah0 + o, idesc, 1u);
         }
     }
 }
@@ -125,8 +165,10 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
     const int row = tid & 127, grp = tid >> 7;
     const int level_cores = P.L / 4;
     const int K0 = P.g.Kp[0];
+    const bool gemm_issuer = lane == 0 && warp < 4;        // stream = warp & 1, column half = warp >> 1
+    const bool dw_issuer = lane == 0 && (warp == 4 || warp == 5);   // column half = warp - 4
 
-    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_init(&bars[2], 1); umma::mbar_fence_init(); }
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 4); umma::mbar_init(&bars[2], 2); umma::mbar_fence_init(); }
     for (int i = tid; i < P.L * 3; i += kBwdThreads) {
         lc->scale[(i / 3) * 4 + (i % 3)] = scale[i];
         lc->shift[(i / 3) * 4 + (i % 3)] = shift ? shift[i] : 0.0f;
@@ -149,6 +191,7 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
 
     const int ntiles = (P.N + kTile - 1) / kTile;
     bool first_tile = true;
+    long long phase_t0 = out.phase_cycles ? clock64() : 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first_tile = false) {
         const int n = tile * kTile + row;
         const bool valid = n < P.N;
@@ -205,6 +248,7 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
             store8(s_X + 2 * kATileBytes, s_X + 3 * kATileBytes, row, kc, ft);
         }
 
+        PSDF_PHASE(kPhEncoder);
         // ---------------- 2. forward recompute, layers 0..2. z_{l+1} | tz_{l+1} -> TMEM columns l * 128 (l = 0, 1) or the work columns (l = 2)
         float g1[16], g2t[16];                 // gelu'(z_3), gelu''(z_3) tz_3 of this thread's chunk: consumed by the first reverse step
         float seed[2][8];                      // upstream gradient columns of this thread (prefetched behind the layer-2 MMAs)
@@ -216,16 +260,18 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
             const uint8_t* at = (l == 1) ? s_Y : s_X;
             uint8_t* dst = (l == 1) ? s_X : s_Y;
             const uint32_t col = (l == 2) ? kColWork : (uint32_t)(l * 128);
-            if (tid == 0) {
+            if (gemm_issuer) {
                 umma::fence_after_sync();
-                if (l == 0) {                  // a_0 | ta_0 leave as they are (needed again for dW_0 at the end of the reverse sweep)
+                if (l == 0 && tid == 0) {      // a_0 | ta_0 leave as they are (needed again for dW_0 at the end of the reverse sweep)
                     umma::bulk_s2g(out.a0_spill + (size_t)tile * kSetBytes, s_X, kSetBytes);
                     umma::bulk_commit();
                 }
-                for (int s = 0; s < 2; s++)
-                    issue_gemm(tmem_base + col + s * 64, at + s * 2 * kATileBytes, at + s * 2 * kATileBytes + kATileBytes, s_w + P.g.w_hi[l],
-                               s_w + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
-                if (l == 1) umma::bulk_wait_read0();       // X is overwritten by this layer's epilogue: the store must have read it
+                const int s = warp & 1;
+                int n0, nn;
+                split_n(P.g.Np[l], warp >> 1, n0, nn);
+                issue_forward_part(tmem_base + col + s * 64, at + s * 2 * kATileBytes, at + s * 2 * kATileBytes + kATileBytes, s_w + P.g.w_hi[l],
+                                   s_w + P.g.w_lo[l], P.g.Kp[l], n0, nn);
+                if (l == 1 && tid == 0) umma::bulk_wait_read0();   // X is overwritten by this layer's epilogue: the store must have read it
                 umma::commit(&bars[1]);
             }
             if (l == 2) {                      // zbar_4 = [g_sdf, g_geom...] columns of this thread, loaded while the MMAs run
@@ -258,6 +304,7 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                 store_set16(dst, row, c, z, tz);
             }
         }
+        PSDF_PHASE(kPhForward);
         // ---------------- 3. seed: zbar_4 = upstream gradient, tzbar_4 = e_0 -> X (a_2 in X is dead: the layer-2 MMAs completed)
         {
             const int Np = P.g.Np[3];
@@ -279,6 +326,7 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                 }
             }
         }
+        PSDF_PHASE(kPhSeed);
         // ---------------- 4. reverse sweep, layers 3..0: X = zbar_{l+1} | tzbar_{l+1}, Y = a_l | ta_l
 #pragma unroll 1
         for (int l = 3; l >= 0; l--) {
@@ -286,19 +334,24 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
             umma::fence_async_smem();
             umma::fence_before_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (gemm_issuer) {
                 umma::fence_after_sync();
-                issue_reverse(tmem_base + kColWork, s_X, s_w + P.g.w_hi[l], s_w + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
+                const int s = warp & 1;
+                int n0, nn;
+                split_n(P.g.Kp[l], warp >> 1, n0, nn);
+                issue_reverse_part(tmem_base + kColWork + s * 64, s_X + s * 2 * kATileBytes, s_X + s * 2 * kATileBytes + kATileBytes,
+                                   s_w + P.g.w_hi[l], s_w + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l], n0, nn);
                 umma::commit(&bars[1]);
-                if (l == 3) {                  // a_3 | ta_3 are in Y since the forward epilogue
-                    issue_dw(dw_col, s_X, s_Y, P.g.Kp[l], first_tile);
-                    umma::commit(&bars[2]);
-                } else if (l == 0) {           // a_0 | ta_0 come back by TMA (requested after the previous step released Y)
-                    umma::mbar_wait(&bars[0], ld_phase);
-                    umma::fence_after_sync();
-                    issue_dw(dw_col, s_X, s_Y, P.g.Kp[l], first_tile);
-                    umma::commit(&bars[2]);
-                }
+            }
+            if (dw_issuer && (l == 3 || l == 0)) {
+                // l = 3: a_3 | ta_3 are in Y since the forward epilogue; l = 0: a_0 | ta_0 come back by TMA (requested after the
+                // previous step released Y)
+                umma::fence_after_sync();
+                if (l == 0) { umma::mbar_wait(&bars[0], ld_phase); umma::fence_after_sync(); }
+                int n0, nn;
+                split_n(P.g.Kp[l], warp - 4, n0, nn);
+                issue_dw_part(dw_col, s_X, s_Y, n0, nn, first_tile);
+                umma::commit(&bars[2]);
             }
             if (l == 1 || l == 2) {
                 // while the reverse MMAs run: rebuild a_l | ta_l -> Y and the GELU' / GELU'' factors from the TMEM-resident z_l, tz_l
@@ -315,9 +368,11 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                 umma::fence_async_smem();
                 umma::fence_before_sync();
                 __syncthreads();
-                if (tid == 0) {
+                if (dw_issuer) {
                     umma::fence_after_sync();
-                    issue_dw(dw_col, s_X, s_Y, P.g.Kp[l], first_tile);
+                    int n0, nn;
+                    split_n(P.g.Kp[l], warp - 4, n0, nn);
+                    issue_dw_part(dw_col, s_X, s_Y, n0, nn, first_tile);
                     umma::commit(&bars[2]);
                 }
             }
@@ -370,6 +425,7 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                     }
                 }
             }
+            PSDF_PHASE(kPhReverse3 + (3 - l));
         }
         ld_phase ^= 1;
         umma::fence_before_sync();
@@ -412,6 +468,8 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
         }
         umma::fence_before_sync();
         __syncthreads();     // exchange tile / TMEM free for the next tile
+        PSDF_PHASE(kPhEncoderBwd);
+        if (out.phase_cycles && tid == 0) atomicAdd(out.phase_cycles + kPhTiles, 1ull);
     }
     // ---------------- weight gradients of this CTA: TMEM -> global (+=). Warp w reads lanes 32 (w & 3) .. +31 of column chunk w >> 2:
     // lanes 0..15 hold rows 16 (w & 3) + lane of the even layer of the pair, lanes 16..31 the same rows of the odd layer
@@ -425,10 +483,17 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
             umma::tmem_ld_wait();
             const int l = 2 * p + (lane >> 4), m = q * 16 + (lane & 15);
             if (m < P.g.N[l]) {
+                const int K = P.g.K[l];
+                float* dst = out.gW[l] + (size_t)m * K + c * 16;
+                const bool vec = (K & 3) == 0 && ((uintptr_t)out.gW[l] & 15) == 0;      // rows stay 16-byte aligned
 #pragma unroll
-                for (int i = 0; i < 16; i++) {
+                for (int i = 0; i < 16; i += 4) {
                     const int k = c * 16 + i;
-                    if (k < P.g.K[l]) atomicAdd(out.gW[l] + (size_t)m * P.g.K[l] + k, acc[i]);
+                    if (vec && k + 3 < K) red_v4(dst + i, acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                    else {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) if (k + j < K) atomicAdd(dst + i + j, acc[i + j]);
+                    }
                 }
             }
         }
@@ -437,6 +502,7 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
         int l = i >> 6, c = i & 63;
         if (c < P.g.N[l] && s_gb[i] != 0.0f) atomicAdd(out.gbias[l] + c, s_gb[i]);
     }
+    PSDF_PHASE(kPhFlush);
     if (tid == 0) umma::bulk_wait0();      // spill stores complete before the CTA retires
     umma::fence_before_sync();
     __syncthreads();
@@ -464,7 +530,7 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
     if (N == 0) return PSDF_OK;
     FusedParams P;
     P.N = N; P.L = L; P.T = T;
-    P.cap_mask = ((T & (T - 1)) == 0) ? (unsigned)(T - 1) : 0u;
+    P.cap_mask = t_magic(T);
     P.points_scaling = points_scaling;
     P.in_dim = (L + 2) * 2;
     if (P.in_dim > 64) return PSDF_ERR_UNSUPPORTED;
@@ -474,6 +540,15 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
     float* b[kNL] = {gb0, gb1, gb2, gb3};
     for (int l = 0; l < kNL; l++) { out.gW[l] = w[l]; out.gbias[l] = b[l]; }
     out.a0_spill = workspace;
+    // diagnostics: PSDF_PHASE_TIMING=1 prints thread 0's clock64 breakdown per phase (average cycles per tile) after every launch
+    static const bool timing = getenv("PSDF_PHASE_TIMING") && atoi(getenv("PSDF_PHASE_TIMING")) != 0;
+    static unsigned long long* d_cycles = nullptr;
+    out.phase_cycles = nullptr;
+    if (timing) {
+        if (!d_cycles) cudaMalloc(&d_cycles, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_cycles, 0, 16 * sizeof(unsigned long long), ST);
+        out.phase_cycles = d_cycles;
+    }
     const int ntiles = div_up(N, kTile);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -484,6 +559,15 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
     k_sdf_fused_backward<<<min(ntiles, sms), kBwdThreads, smem, ST>>>(P, pos, reinterpret_cast<const float2*>(lattice), scale_factor, shift,
                                                                       window, blob, g_sdf, g_grad, g_geom, grad_lattice, out);
     PSDF_CHECK_LAUNCH();
+    if (timing) {
+        unsigned long long h[16];
+        cudaMemcpyAsync(h, d_cycles, sizeof(h), cudaMemcpyDeviceToHost, ST);
+        cudaStreamSynchronize(ST);
+        const double t = h[kPhTiles] ? (double)h[kPhTiles] : 1.0;
+        fprintf(stderr, "[psdf_sdf_fused_backward N=%d tiles=%llu] cycles/tile: encoder %.0f forward %.0f seed %.0f rev3 %.0f rev2 %.0f rev1 %.0f rev0 %.0f "
+                        "encoder_bwd %.0f | flush/CTA %.0f\n", N, h[kPhTiles], h[0] / t, h[1] / t, h[2] / t, h[3] / t, h[4] / t, h[5] / t, h[6] / t, h[7] / t,
+                (double)h[kPhFlush] / min(ntiles, sms));
+    }
     return PSDF_OK;
 }
 

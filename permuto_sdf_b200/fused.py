@@ -118,7 +118,7 @@ def _fused_sdf_sphere_trace(self, points, dirs, iter_nr, nr_iters, sdf_multiplie
     N = pts.shape[0]
     out = torch.empty_like(pts)
     conv = torch.empty(N, dtype=torch.bool, device=pts.device)
-    queue = torch.zeros(2, dtype=torch.int32, device=pts.device)        # [0] ray queue of the persistent CTAs, [1] evaluation count
+    queue = torch.zeros(8, dtype=torch.int32, device=pts.device)        # [0] ray queue of the persistent CTAs, [1..4] statistics
     self.last_trace_stats = queue
     window = m.window(iter_nr).view(-1).contiguous()
     sph = m.boundary_primitive

@@ -1,0 +1,46 @@
+"""The reference-Python fixture (tests/golden/refpy_golden.npz) is reproducible: where /root/reference exists (the build container)
+the committed generator, run again, must give the committed arrays. Also checks the fixture's internal consistency everywhere."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+FIX = os.path.join(HERE, "golden", "refpy_golden.npz")
+
+
+def test_fixture_is_complete():
+    G = np.load(FIX)
+    keys = set(G.keys())
+    for need in ("sdf_out.sdf", "sdf_grad.lattice_rows", "curv_out.curvature", "rgb_out.rgb", "rgb_grad.mlp.lipshitz_bound_per_layer.0",
+                 "rgb_grad.cal.weight_delta", "bg_out.density", "neus_free.weights", "neus_forced.g_sdf", "imp_out.samples_z", "trace_out.points"):
+        assert need in keys, need
+    # the reference's state_dict key names travel with the fixture (checkpoint interoperability)
+    assert {"rgb.mlp.weights_per_layer.0", "rgb.mlp.biases_per_layer.3", "rgb.mlp.layers.2.weight", "rgb.mlp.lipshitz_bound_per_layer.1",
+            "rgb.volume_renderer_neus.deviation_network.variance", "sdf.mlp_sdf.6.bias", "sdf.encoding.random_shift_per_level"} <= keys
+    se = G["rgb_in.ray_start_end_idx"]
+    assert (se[:, 1] >= se[:, 0]).all() and (se[3, 1] == se[3, 0]) and se[-1, 1] == G["rgb_in.points"].shape[0]
+    # the Lipschitz clamp is active in the fixture: softplus(c) below at least one row sum of |W| in a layer
+    for l in range(4):
+        w, c = G["rgb.mlp.layers.%d.weight" % l], float(G["rgb.mlp.lipshitz_bound_per_layer.%d" % l][0])
+        if np.log1p(np.exp(c)) < np.abs(w).sum(1).max():
+            break
+    else:
+        pytest.fail("no active Lipschitz clamp in the fixture")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/permuto_sdf_py"), reason="the reference's Python exists only in the build container")
+def test_fixture_regenerates_from_the_reference(tmp_path):
+    env = dict(os.environ, REFPY_GOLDEN_OUT=str(tmp_path / "again.npz"))
+    r = subprocess.run([sys.executable, os.path.join(HERE, "golden", "make_refpy_golden.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    a, b = np.load(FIX), np.load(str(tmp_path / "again.npz"))
+    assert set(a.keys()) == set(b.keys())
+    for k in a.keys():
+        if a[k].dtype.kind == "f":
+            assert np.allclose(a[k], b[k], rtol=1e-5, atol=1e-7), k
+        else:
+            assert np.array_equal(a[k], b[k]), k

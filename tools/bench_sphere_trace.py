@@ -42,9 +42,9 @@ def main():
     u, v = torch.meshgrid(torch.arange(W, device="cuda", dtype=torch.float32), torch.arange(H, device="cuda", dtype=torch.float32), indexing="xy")
     # pixel centres (u + 0.5): no ray has an exactly zero direction component -- such rays creep by 1e-6 per DDA step in the reference's
     # marchers (reproduced here) and would dominate the frame time
-    d = torch.stack([(u + 0.5 - W / 2) / f, (v + 0.5 - H / 2) / f, -torch.ones_like(u)], -1).reshape(-1, 3)
+    d = torch.stack([(u + 0.5 - W / 2) / f, (v + 0.5 - H / 2) / f, torch.ones_like(u)], -1).reshape(-1, 3)
     d = torch.nn.functional.normalize(d, dim=-1).contiguous()
-    o = torch.tensor([0.0, 0.0, 1.5], device="cuda").expand_as(d).contiguous()
+    o = torch.tensor([0.0, 0.0, -1.5], device="cuda").expand_as(d).contiguous()
     out = {}
     torch.set_grad_enabled(False)          # rendering: every network evaluation takes the fused tcgen05 path
     tr.FUSED_SPHERE_TRACE_MAX_RAYS = 1 << 30          # compare both paths at every size
