@@ -168,17 +168,21 @@ def run_ours(args):
     pix_dev = [p.to(dev) for p in pix_host]
     img_dev = [p.to(dev) for p in img_host]
 
+    dp_mode = os.environ.get("PSDF_DP_MODE", "peer")        # peer | nccl | nccl_overlap | legacy
+    if world > 1 and flat is None and dp_mode != "legacy":
+        # peer: fused gradient reduction + AdamW + parameter broadcast over NVLink peer memory (no all-reduce); nccl: one all-reduce
+        # captured in the optimizer graph; nccl_overlap: bucketed all-reduce overlapped with the SDF backward / AdamW
+        tr.enable_data_parallel(world, overlap=(dp_mode == "nccl_overlap"), mode="peer" if dp_mode == "peer" else "nccl")
+
     def one_step(i, e2e):
         # e2e: the step's inputs start in pinned host memory; otherwise they are device resident
         pix, img = (pix_host[i], img_host[i]) if e2e else (pix_dev[i], img_dev[i])
-        loss = tr.step_from_reel(reel, pix, img, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1))
-        if world > 1:
-            # the single collective of the path: one NCCL all-reduce of the flat gradient buffer, mean folded into AdamW
-            if flat is None and os.environ.get("PSDF_NCCL_IN_GRAPH", "0") == "1":
-                tr.optimizer_step(grad_scale=1.0 / world, allreduce=True)       # captured in the optimizer graph
-            else:
-                dist.all_reduce(tr.optimizer.flat_grad if flat is None else flat.flat, op=dist.ReduceOp.SUM)
-                tr.optimizer_step(grad_scale=1.0 / world)
+        dp = tr._dp is not None
+        loss = tr.step_from_reel(reel, pix, img, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1 or dp))
+        if world > 1 and not dp:
+            # legacy path (PSDF_DP_MODE=legacy): one blocking NCCL all-reduce of the flat gradient buffer between the two graphs
+            dist.all_reduce(tr.optimizer.flat_grad if flat is None else flat.flat, op=dist.ReduceOp.SUM)
+            tr.optimizer_step(grad_scale=1.0 / world)
         if e2e:
             return float(loss)          # device -> host read of the step's result
         return loss
@@ -275,7 +279,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "ours",
             "config": {"workload": WORKLOAD if NR_RAYS == 512 else WORKLOAD.replace("512 rays", "%d rays" % NR_RAYS).replace("C2:", "C2 shape at %d rays/GPU (BASELINE config 4 when 8192 x 8 GPUs):" % NR_RAYS),
-                       "rays_per_gpu": NR_RAYS, "avg_samples_per_step": avg_samples, "parallelism": "dp%d" % world,
+                       "rays_per_gpu": NR_RAYS, "avg_samples_per_step": avg_samples, "parallelism": "dp%d" % world, "gradient_exchange": (dp_mode if world > 1 else None),
                        "l2": "per-step working set (2 lattice tables + grads + Adam moments ~0.4 GB) exceeds the 126 MB L2; no explicit flush",
                        "timed_region": "sum of per-step CUDA-event intervals",
                        "execution": "eager" if (args.modular or args.eager) else "CUDA graphs (forward+backward graph, optimizer graph), static-capacity containers"},

@@ -286,6 +286,19 @@ int psdf_adamw_step(long long n, float* param, float* grad, float* exp_avg, floa
                     float eps, float weight_decay, int step, const int* step_dev, const float* hyper_dev, float grad_scale, int zero_grad,
                     void* stream);
 
+/* Data-parallel step without NCCL: gradient reduction + AdamW + parameter broadcast in ONE kernel over NVLink peer memory. This rank
+ * owns the elements [shard_lo, shard_lo + n) of the group (both multiples of 4): it sums that shard of ALL ranks' gradient buffers
+ * (peer loads), updates its local moments and writes the new parameters into ALL ranks' parameter buffers (peer stores).
+ * grad_ptrs / param_ptrs: HOST arrays of `world` <= 8 device pointers (rank r's buffer of this group, peer-mapped here, e.g.
+ * torch.distributed._symmetric_memory); mc_grad_ptr / mc_param_ptr: the NVSwitch MULTICAST mapping of the same two buffers (group base),
+ * or 0: when given, the reduction is one multimem.ld_reduce (summed in the switch) and the broadcast one multimem.st per 16 bytes;
+ * exp_avg / exp_avg_sq: local, full group size. world in {1, 2, 4, 8}. The caller puts a cross-rank barrier before
+ * (gradients final) and after (parameters landed) the call and zeroes its own gradients afterwards. Replaces all-reduce + AdamW of
+ * the reference's (non-existent) data-parallel loop: SURVEY.md 8(e). */
+int psdf_adamw_dp_step(long long n, long long shard_lo, int world, int rank, const uint64_t* grad_ptrs, const uint64_t* param_ptrs,
+                       uint64_t mc_grad_ptr, uint64_t mc_param_ptr, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int step, const int* step_dev, const float* hyper_dev, float grad_scale, void* stream);
+
 /* self-test of the tensor-core path: D[128,N] = A[128,K] * B[N,K]^T (N,K <= 64) */
 int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream);
 /* self-test of the weight-gradient product: D[M,N] = A[128,M]^T * B[128,N] (M,N <= 64) with the sample axis as the MMA K

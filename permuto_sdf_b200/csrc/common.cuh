@@ -280,6 +280,16 @@ __device__ __forceinline__ int occ_advance_resumable(const GridGeom& g, const ui
     }
     return ((double)steps < max_steps) ? 0 : 1;
 }
+// one-time (per device and kernel) opt-in to more than 48 KB of dynamic shared memory; `slot` is a static array owned by the call site
+template <typename K>
+inline void psdf_optin_smem(K kernel, int bytes, bool (&slot)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !slot[dev]) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (dev >= 0 && dev < 64) slot[dev] = true;
+    }
+}
 inline GridGeom make_grid_geom(int V, float extent, const float* t) {
     GridGeom g;
     g.V = V; g.extent = extent; g.tx = t[0]; g.ty = t[1]; g.tz = t[2];

@@ -170,6 +170,8 @@ struct FusedParams {
     unsigned cap_mask;   // t_magic(T): multiplier of the division-free h mod T (any capacity, not only powers of two)
     float points_scaling;
     int in_dim;          // (L + E) * 2 feature columns
+    int free_levels = 0; // diagnostics only (PSDF_EXPERIMENT_FREE_LEVELS): the gathers of levels < free_levels read nothing (upper bound of
+                         // what staging those levels' table entries in shared memory could save); 0 in production
     MlpGeom g;
 };
 

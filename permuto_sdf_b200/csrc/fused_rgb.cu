@@ -32,7 +32,7 @@ k_rgb_fused(RgbParams P, const float* __restrict__ pos, const float* __restrict_
 
     const int tid = threadIdx.x, warp = tid >> 5;
     const int row = tid & 127, grp = tid >> 7;
-    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 4); umma::mbar_fence_init(); }
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }
     load_level_consts(lc, P.L, scale, shift, window, tid, kRgbThreads);
     for (int i = tid; i < kNL * 128; i += kRgbThreads) {
         int l = i >> 7, c = i & 127;
@@ -60,11 +60,9 @@ k_rgb_fused(RgbParams P, const float* __restrict__ pos, const float* __restrict_
             umma::fence_async_smem();
             umma::fence_before_sync();
             __syncthreads();
-            if ((tid & 31) == 0 && warp < 4) {
+            if (tid == 0) {
                 umma::fence_after_sync();
-                int n0, nn;
-                split4(P.g.Np[l], warp, n0, nn);
-                issue_gemm_w_part(tmem_base, s_a, s_a + kWTileBytes, s_w, s_w + P.g.Np[l] * P.g.Kp[l] * 2, P.g.Kp[l], n0, nn);
+                issue_gemm_w(tmem_base, s_a, s_a + kWTileBytes, s_w, s_w + P.g.Np[l] * P.g.Kp[l] * 2, P.g.Kp[l], P.g.Np[l]);
                 umma::commit(&bars[1]);
             }
             umma::mbar_wait(&bars[1], mma_phase);
@@ -136,7 +134,7 @@ int psdf_rgb_fused_forward(int N, int L, int T, const float* pos, const float* d
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = (size_t)4 * kWTileBytes + sizeof(LevelC) + kNL * 128 * sizeof(float) + 64;
-    cudaFuncSetAttribute(k_rgb_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      // per device: set on every call (a second GPU needs its own opt-in)
+    { static bool optin_[64]; psdf::psdf_optin_smem(k_rgb_fused, 227 * 1024, optin_); }
     const int ntiles = div_up(N, kTile);
     k_rgb_fused<<<min(ntiles, sms), kRgbThreads, smem, ST>>>(P, pos, dirs, sdf_grad, geom, reinterpret_cast<const float2*>(lattice),
                                                              scale_factor, shift, window, blob, out);

@@ -51,7 +51,7 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & 127, grp = tid >> 7;
     const int K0 = P.g.Kp[0];
-    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 4); umma::mbar_fence_init(); }
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }
     load_level_consts(lc, P.L, scale, shift, window, tid, kRgbThreads);
     for (int i = tid; i < kNL * 128; i += kRgbThreads) {
         int l = i >> 7, c = i & 127;
@@ -84,16 +84,12 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
             umma::fence_async_smem();
             umma::fence_before_sync();
             __syncthreads();
-            if (lane == 0 && warp < 4) {       // four issuing threads, a quarter of the accumulator columns each
+            if (tid == 0) {
                 umma::fence_after_sync();
-                if (tid == 0) {
-                    umma::bulk_s2g(sp.at[l] + (size_t)tile * kRgbSpillBytes, s_a, kRgbSpillBytes);      // a_l for dW_l
-                    umma::bulk_commit();
-                }
-                int n0, nn;
-                split4(P.g.Np[l], warp, n0, nn);
-                issue_gemm_w_part(tmem_z[l], s_a, s_a + kWTileBytes, s_w, s_w + P.g.Np[l] * P.g.Kp[l] * 2, P.g.Kp[l], n0, nn);
-                if (tid == 0) umma::bulk_wait_read0();
+                umma::bulk_s2g(sp.at[l] + (size_t)tile * kRgbSpillBytes, s_a, kRgbSpillBytes);      // a_l for dW_l
+                umma::bulk_commit();
+                issue_gemm_w(tmem_z[l], s_a, s_a + kWTileBytes, s_w, s_w + P.g.Np[l] * P.g.Kp[l] * 2, P.g.Kp[l], P.g.Np[l]);
+                umma::bulk_wait_read0();
                 umma::commit(&bars[1]);
             }
             umma::mbar_wait(&bars[1], mma_phase);
@@ -130,18 +126,14 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
             umma::fence_async_smem();
             umma::fence_before_sync();
             __syncthreads();
-            if (lane == 0 && warp < 4) {
+            if (tid == 0) {
                 umma::fence_after_sync();
-                if (tid == 0) {
-                    umma::bulk_s2g(sp.zt[l] + (size_t)tile * kRgbSpillBytes, s_z, kRgbSpillBytes);       // zbar^(l) for dW_l
-                    if (l == 3) umma::bulk_s2g(sp.at[3] + (size_t)tile * kRgbSpillBytes, s_a, kRgbSpillBytes);   // a_3
-                    umma::bulk_commit();
-                }
+                umma::bulk_s2g(sp.zt[l] + (size_t)tile * kRgbSpillBytes, s_z, kRgbSpillBytes);       // zbar^(l) for dW_l
+                if (l == 3) umma::bulk_s2g(sp.at[3] + (size_t)tile * kRgbSpillBytes, s_a, kRgbSpillBytes);   // a_3
+                umma::bulk_commit();
                 // abar_l [128 x Kp_l] = zbar^(l) [128 x Np_l] W_l : B operand = W_l^T stored [Kp_l rows][Np_l]
-                int n0, nn;
-                split4(P.g.Kp[l], warp, n0, nn);
-                issue_gemm_w_part(tmem_work, s_z, s_z + kWTileBytes, s_w, s_w + P.g.Np[l] * P.g.Kp[l] * 2, P.g.Np[l], n0, nn);
-                if (tid == 0) umma::bulk_wait_read0();
+                issue_gemm_w(tmem_work, s_z, s_z + kWTileBytes, s_w, s_w + P.g.Np[l] * P.g.Kp[l] * 2, P.g.Np[l], P.g.Kp[l]);
+                umma::bulk_wait_read0();
                 umma::commit(&bars[1]);
             }
             // while the MMAs run: gelu'(z^(l-1)) of this thread's column chunks from the TMEM-resident pre-activations
@@ -409,8 +401,8 @@ int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = (size_t)6 * kWTileBytes + sizeof(LevelC) + 2 * kNL * 128 * sizeof(float) + 64;
     // per device: set on every call (a second GPU needs its own opt-in)
-    cudaFuncSetAttribute(k_rgb_fused_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(k_rgb_dw, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    { static bool optin_[64]; psdf::psdf_optin_smem(k_rgb_fused_backward, 227 * 1024, optin_); }
+    { static bool optin_[64]; psdf::psdf_optin_smem(k_rgb_dw, 227 * 1024, optin_); }
     const size_t smem_dw = (size_t)kDwStages * kDwStageBytes + 128;
     for (int t0 = 0; t0 < ntiles; t0 += chunk) {
         const int nt = min(chunk, ntiles - t0);

@@ -84,29 +84,6 @@ __device__ __forceinline__ void issue_gemm_w(uint32_t tmem_d, const uint8_t* a_h
     }
 }
 
-// The MMA sequence of a layer is issued by four threads (lane 0 of warps 0..3, one per SM sub-partition), each owning a quarter of the
-// accumulator columns (in units of 16): the single-thread issue latency shrinks four-fold; all four commit to the layer's mbarrier.
-__device__ __forceinline__ void split4(int N, int part, int& n0, int& nn) {
-    const int u = N / 16, base = u / 4, rem = u % 4;
-    n0 = (part * base + (part < rem ? part : rem)) * 16;
-    nn = (base + (part < rem ? 1 : 0)) * 16;
-}
-__device__ __forceinline__ void issue_gemm_w_part(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
-                                                  const uint8_t* w_lo, int Kp, int n0, int nn) {
-    if (nn <= 0) return;
-    const uint32_t idesc = umma::make_idesc(128, nn, umma::kFmtBF16);
-    const uint32_t sbo_w = (Kp / 8) * kLBO;
-    const uint32_t woff = (n0 / 8) * sbo_w;
-    const uint64_t dah0 = umma::make_desc(umma::smem_u32(a_hi), kLBO, kWSBO), dal0 = umma::make_desc(umma::smem_u32(a_lo), kLBO, kWSBO);
-    const uint64_t dwh0 = umma::make_desc(umma::smem_u32(w_hi) + woff, kLBO, sbo_w), dwl0 = umma::make_desc(umma::smem_u32(w_lo) + woff, kLBO, sbo_w);
-    for (int kk = 0; kk < Kp / 16; kk++) {
-        const uint64_t off = (uint64_t)(kk * ((2 * kLBO) >> 4));
-        umma::mma_bf16(tmem_d + n0, dah0 + off, dwh0 + off, idesc, kk > 0 ? 1u : 0u);
-        umma::mma_bf16(tmem_d + n0, dah0 + off, dwl0 + off, idesc, 1u);
-        umma::mma_bf16(tmem_d + n0, dal0 + off, dwh0 + off, idesc, 1u);
-    }
-}
-
 // Layer-0 operand tile of one sample row. Thread (row, grp) builds the 8-column cores grp, grp+4, ... of the lattice part and
 // the two tail cores T_grp, T_{grp+4} (tail = concat points | SH | normal | geom, 64 columns = 8 cores after column 2L).
 __device__ __forceinline__ void build_input_tile(const RgbParams& P, const LevelC* lc, const float2* __restrict__ lattice,

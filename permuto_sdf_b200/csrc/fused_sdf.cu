@@ -21,21 +21,27 @@
 //             tcgen05.ld, bias, GELU / GELU', bf16 hi/lo split, 16-byte core stores for the next layer.
 // Weights (hi+lo, pre-packed in the UMMA core-matrix layout by k_pack_mlp) are fetched once per CTA with one
 // cp.async.bulk (TMA) and stay resident; CTAs are persistent over tiles (one CTA per SM).
+#include <cstdlib>
 #include "fused_common.cuh"
 #include "../../include/psdf_b200.h"
 
 using namespace psdf_fused;
 
 namespace {
+// Threads per CTA. The value + tangent kernel needs 186 KB of shared memory (one CTA per SM, 512 threads = 4 per sample row). The
+// value-only kernels (inference forward, sphere tracer) need 93 KB: with 256 threads (2 per row, <= 128 registers) TWO CTAs share an
+// SM, each on its own tile with its own barriers, so that one CTA's MMA / barrier / gather waits are filled by the other's work.
 constexpr int kFusedThreads = 512;
-constexpr int kGroups = kFusedThreads / kTile;
+constexpr int kValueThreads = 256;
+template <bool TAN> struct FwdCfg { static constexpr int kThreads = TAN ? kFusedThreads : kValueThreads; static constexpr int kCtasPerSm = TAN ? 1 : 2; };
 
 template <bool TAN>
-__global__ void __launch_bounds__(kFusedThreads, 1)
+__global__ void __launch_bounds__(FwdCfg<TAN>::kThreads, FwdCfg<TAN>::kCtasPerSm)
 k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restrict__ lattice, const float* __restrict__ scale,
             const float* __restrict__ shift, const float* __restrict__ window, const uint8_t* __restrict__ blob,
             float* __restrict__ sdf_out, float* __restrict__ grad_out, float* __restrict__ geom_out) {
     constexpr int S = TAN ? 4 : 1;
+    constexpr int kThreads = FwdCfg<TAN>::kThreads, kGroups = kThreads / kTile;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_blob = smem;
     uint8_t* s_a = smem + P.g.total;                       // S streams x {hi, lo} x 16 KB
@@ -50,11 +56,11 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
         umma::mbar_init(&bars[1], S);          // one tcgen05.commit per issuing thread (one per stream)
         umma::mbar_fence_init();
     }
-    for (int i = tid; i < P.L * 3; i += kFusedThreads) {
+    for (int i = tid; i < P.L * 3; i += kThreads) {
         lc->scale[(i / 3) * 4 + (i % 3)] = scale[i];
         lc->shift[(i / 3) * 4 + (i % 3)] = shift ? shift[i] : 0.0f;
     }
-    for (int i = tid; i < P.L; i += kFusedThreads) lc->window[i] = window ? window[i] : 1.0f;
+    for (int i = tid; i < P.L; i += kThreads) lc->window[i] = window ? window[i] : 1.0f;
     __syncthreads();
     if (warp == 0) umma::tmem_alloc(tmem_slot, S * 64);
     if (tid == 0) {
@@ -94,7 +100,10 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
                     const float2* tab = lattice + (size_t)l * P.T;
                     float2 v[4];
 #pragma unroll
-                    for (int r = 0; r < 4; r++) v[r] = __ldg(tab + vindex3(s, r, P.cap_mask, (unsigned)P.T));
+                    for (int r = 0; r < 4; r++) {
+                        const unsigned vi = vindex3(s, r, P.cap_mask, (unsigned)P.T);
+                        v[r] = (l < P.free_levels) ? make_float2(1e-6f * (float)(vi & 7u), 0.f) : __ldg(tab + vi);
+                    }
                     const float w = lc->window[l];
                     float a0 = 0.f, a1 = 0.f;
 #pragma unroll
@@ -165,8 +174,7 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
             const float* bias = reinterpret_cast<const float*>(s_blob + P.g.bias[l]);
             const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
             const bool last = (l == kNL - 1);
-            const int c = grp;                                  // this thread's 16-column chunk
-            if (c < P.g.Np[l] / 16) {
+            for (int c = grp; c < P.g.Np[l] / 16; c += kGroups) {     // this thread's 16-column chunks
                 float z[16], tz[3][16];
                 umma::tmem_ld16(trow + c * 16, z);
                 if (TAN) {
@@ -234,7 +242,7 @@ struct TraceParams {
     psdf::GridGeom grid;
     float sph_radius, sph_cx, sph_cy, sph_cz;
 };
-__global__ void __launch_bounds__(kFusedThreads, 1)
+__global__ void __launch_bounds__(kValueThreads, 2)
 k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_in, const float* __restrict__ dirs,
                    const float2* __restrict__ lattice, const float* __restrict__ scale, const float* __restrict__ shift,
                    const float* __restrict__ window, const uint8_t* __restrict__ blob, const uint8_t* __restrict__ occ,
@@ -259,12 +267,13 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & (kTile - 1), grp = tid >> 7;
+    constexpr int kGroups = kValueThreads / kTile;
     if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); s_flag[0] = 0; }
-    for (int i = tid; i < P.L * 3; i += kFusedThreads) {
+    for (int i = tid; i < P.L * 3; i += kValueThreads) {
         lc->scale[(i / 3) * 4 + (i % 3)] = scale[i];
         lc->shift[(i / 3) * 4 + (i % 3)] = shift ? shift[i] : 0.0f;
     }
-    for (int i = tid; i < P.L; i += kFusedThreads) lc->window[i] = window ? window[i] : 1.0f;
+    for (int i = tid; i < P.L; i += kValueThreads) lc->window[i] = window ? window[i] : 1.0f;
     __syncthreads();
     if (warp == 0) umma::tmem_alloc(tmem_slot, 64);
     if (tid == 0) {
@@ -364,9 +373,8 @@ k_sdf_sphere_trace(FusedParams P, TraceParams Q, const float* __restrict__ pos_i
                 umma::fence_after_sync();
                 const float* bias = reinterpret_cast<const float*>(s_blob + P.g.bias[l]);
                 const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-                const int c = grp;
                 if (l < kNL - 1) {
-                    if (c < P.g.Np[l] / 16) {
+                    for (int c = grp; c < P.g.Np[l] / 16; c += kGroups) {
                         float z[16];
                         umma::tmem_ld16(trow + c * 16, z);
                         umma::tmem_ld_wait();
@@ -624,9 +632,9 @@ int psdf_sdf_sphere_trace(int N, int L, int T, const float* pos, const float* di
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + kTile * 11 * sizeof(float) + 96;
-    cudaFuncSetAttribute(k_sdf_sphere_trace, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_sphere_trace, 227 * 1024, optin_); }
     const int ntiles = div_up(N, kTile);
-    k_sdf_sphere_trace<<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, Q, pos, dirs, reinterpret_cast<const float2*>(lattice), scale_factor,
+    k_sdf_sphere_trace<<<min(ntiles, 2 * sms), kValueThreads, smem, ST>>>(P, Q, pos, dirs, reinterpret_cast<const float2*>(lattice), scale_factor,
                                                                      shift, window, blob, occupancy, pos_out, converged, queue_counter);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
@@ -667,6 +675,8 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
     P.points_scaling = points_scaling;
     P.in_dim = (L + 2) * 2;                       // D = 3, F = 2: E = 2 concat levels
     if (P.in_dim > 64) return PSDF_ERR_UNSUPPORTED;
+    static const int free_levels = getenv("PSDF_EXPERIMENT_FREE_LEVELS") ? atoi(getenv("PSDF_EXPERIMENT_FREE_LEVELS")) : 0;
+    P.free_levels = free_levels;
     P.g = make_geom(P.in_dim, hidden, out_dim);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -675,12 +685,12 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
     const float2* lat = reinterpret_cast<const float2*>(lattice);
     if (grad) {
         size_t smem = (size_t)P.g.total + 4 * 2 * kATileBytes + sizeof(LevelC) + 64;
-        cudaFuncSetAttribute(k_sdf_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);      // per device: set on every call (a second GPU needs its own opt-in)
+        { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_fused<true>, 227 * 1024, optin_); }
         k_sdf_fused<true><<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
     } else {
         size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + 64;
-        cudaFuncSetAttribute(k_sdf_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024);      // per device: set on every call (a second GPU needs its own opt-in)
-        k_sdf_fused<false><<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
+        { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_fused<false>, 113 * 1024, optin_); }
+        k_sdf_fused<false><<<min(ntiles, 2 * sms), kValueThreads, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
     }
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
@@ -689,7 +699,7 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
 int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream) {
     if (N < 1 || N > 64 || K < 1 || K > 64) return PSDF_ERR_ARG;
     size_t smem = 2 * kATileBytes + 2 * (size_t)pad16(N) * pad16(K) * 2 + 64;
-    cudaFuncSetAttribute(k_debug_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    { static bool optin_[64]; psdf::psdf_optin_smem(k_debug_gemm, 100 * 1024, optin_); }
     k_debug_gemm<<<1, kTile, smem, ST>>>(N, K, A, B, D);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;

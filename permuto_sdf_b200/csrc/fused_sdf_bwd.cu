@@ -84,10 +84,12 @@ __device__ __forceinline__ void store_set16(uint8_t* set, int row, int c, const 
     store8(set + 2 * kATileBytes, set + 3 * kATileBytes, row, 2 * c + 1, ta + 8);
 }
 
-// The tcgen05.mma sequences of a phase are issued by several threads (lane 0 of warps 0..3 for the forward / reverse GEMMs, of warps
-// 4..5 for the weight gradients): each issuer owns a disjoint slice of the accumulator columns (stream x half of N), so the
-// single-thread issue latency is divided by the number of issuers and runs on different SM sub-partitions; every issuer commits
-// to the phase's mbarrier (initialised with the issuer count).
+// The tcgen05.mma sequences of a phase are issued by several threads: lane 0 of warps 0 / 1 issues the value / tangent stream of the
+// forward and reverse GEMMs, lane 0 of warps 4 / 5 one half of the weight-gradient columns each. Every issuer owns its accumulator
+// columns, the single-thread issue sequences run side by side on different SM sub-partitions, and each issuer commits to the phase's
+// mbarrier (initialised with the issuer count). Streams are NOT split along N: a shared-memory-operand MMA re-reads its whole A tile
+// (128 x 16 bf16 = 4 KB) whatever N is, so narrower MMAs only multiply the A traffic (measured: the colour network, split four ways
+// along N, got 30 % slower).
 __device__ __forceinline__ void split_n(int N, int half, int& n0, int& nn) {      // halves in units of 16 columns (MMA N % 16 == 0)
     const int na = ((N / 16 + 1) / 2) * 16;
     n0 = half ? na : 0;
@@ -165,10 +167,10 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
     const int row = tid & 127, grp = tid >> 7;
     const int level_cores = P.L / 4;
     const int K0 = P.g.Kp[0];
-    const bool gemm_issuer = lane == 0 && warp < 4;        // stream = warp & 1, column half = warp >> 1
+    const bool gemm_issuer = lane == 0 && warp < 2;        // stream = warp
     const bool dw_issuer = lane == 0 && (warp == 4 || warp == 5);   // column half = warp - 4
 
-    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 4); umma::mbar_init(&bars[2], 2); umma::mbar_fence_init(); }
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 2); umma::mbar_init(&bars[2], 2); umma::mbar_fence_init(); }
     for (int i = tid; i < P.L * 3; i += kBwdThreads) {
         lc->scale[(i / 3) * 4 + (i % 3)] = scale[i];
         lc->shift[(i / 3) * 4 + (i % 3)] = shift ? shift[i] : 0.0f;
@@ -266,11 +268,9 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
                     umma::bulk_s2g(out.a0_spill + (size_t)tile * kSetBytes, s_X, kSetBytes);
                     umma::bulk_commit();
                 }
-                const int s = warp & 1;
-                int n0, nn;
-                split_n(P.g.Np[l], warp >> 1, n0, nn);
+                const int s = warp;
                 issue_forward_part(tmem_base + col + s * 64, at + s * 2 * kATileBytes, at + s * 2 * kATileBytes + kATileBytes, s_w + P.g.w_hi[l],
-                                   s_w + P.g.w_lo[l], P.g.Kp[l], n0, nn);
+                                   s_w + P.g.w_lo[l], P.g.Kp[l], 0, P.g.Np[l]);
                 if (l == 1 && tid == 0) umma::bulk_wait_read0();   // X is overwritten by this layer's epilogue: the store must have read it
                 umma::commit(&bars[1]);
             }
@@ -336,11 +336,9 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
             __syncthreads();
             if (gemm_issuer) {
                 umma::fence_after_sync();
-                const int s = warp & 1;
-                int n0, nn;
-                split_n(P.g.Kp[l], warp >> 1, n0, nn);
+                const int s = warp;
                 issue_reverse_part(tmem_base + kColWork + s * 64, s_X + s * 2 * kATileBytes, s_X + s * 2 * kATileBytes + kATileBytes,
-                                   s_w + P.g.w_hi[l], s_w + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l], n0, nn);
+                                   s_w + P.g.w_hi[l], s_w + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l], 0, P.g.Kp[l]);
                 umma::commit(&bars[1]);
             }
             if (dw_issuer && (l == 3 || l == 0)) {
@@ -555,7 +553,7 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = (size_t)P.g.total + 2 * kSetBytes + sizeof(LevelC) + kNL * 64 * sizeof(float) + 64;
     if ((size_t)128 * (2 * P.g.Kp[0] + 1) * 4 > (size_t)2 * kSetBytes || smem > 227 * 1024) return PSDF_ERR_UNSUPPORTED;
-    cudaFuncSetAttribute(k_sdf_fused_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);   // per device: cheap, not cached
+    { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_fused_backward, 227 * 1024, optin_); }
     k_sdf_fused_backward<<<min(ntiles, sms), kBwdThreads, smem, ST>>>(P, pos, reinterpret_cast<const float2*>(lattice), scale_factor, shift,
                                                                       window, blob, g_sdf, g_grad, g_geom, grad_lattice, out);
     PSDF_CHECK_LAUNCH();

@@ -216,6 +216,10 @@ class _NeusRenderLossFn(torch.autograd.Function):
         cos_dev = cos_anneal.detach().reshape(1).float().contiguous() if isinstance(cos_anneal, torch.Tensor) else None
         cos_f = 0.0 if cos_dev is not None else float(cos_anneal)
         n_dev = rsp.cur_nr_samples if RaySamplesPacked.static_capacity else None
+        # data-parallel runs: the eikonal term is a mean over the samples of ALL ranks -> divide by the mean per-rank sample count
+        # (set by train.run_net after an 8-byte all-reduce) instead of the local one, so that the rank-averaged gradient equals the
+        # gradient of the global batch
+        n_dev = getattr(rsp, "dp_mean_nr_samples", None) if getattr(rsp, "dp_mean_nr_samples", None) is not None else n_dev
         call("psdf_neus_render_loss_forward", *rsp._rsp(), sdf_c, grad_c, rgb_c, rsp.samples_dirs, rsp.samples_dt, inv_s_c, cos_f, cos_dev,
              gt_rgb, gt_mask, hit, bg_c, alpha, T, w, pred, wsum, bgT, ray_loss)
         terms = ray_loss.sum(0)
@@ -403,6 +407,8 @@ class _FusedRGBTrainFn(torch.autograd.Function):
         call("psdf_rgb_fused_backward", N, enc.nr_levels, enc.capacity, points, dirs, sg, gm, gm.shape[1], lattice.detach(), enc.scale_factor,
              enc.shift_tensor(), window, enc.concat_points_scaling, *fr.h, fr.blob, g_out.contiguous(), g_lat, g_sg, g_gm, ws, gW[0], gW[1],
              gW[2], gW[3], gb[0], gb[1], gb[2], gb[3])
+        if in_place and getattr(fr, "after_backward", None) is not None:
+            fr.after_backward()          # data-parallel: the colour hash-table gradient is final -> its all-reduce starts now
         if in_place:
             return (None, None, g_sg, g_gm, None, gW[0], None, gW[1], None, gW[2], None, gW[3], None, None, None)
         return (None, None, g_sg, g_gm, g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)

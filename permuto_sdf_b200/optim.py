@@ -37,6 +37,7 @@ class FusedAdamW:
         self.step_dev = None
         self._clean = True              # flat_grad is known to be all zero (fresh, or just swept by the step kernel)
         self.hyper_dev = None           # [groups, 2] device copy of (lr, weight_decay), read by the kernel in device_step mode
+        self._peer = None               # data-parallel peer-memory step (enable_peer_step)
         self._hyper_host = None
         self._hyper_cached = None
         for g, (ps, off, n, n_pad) in zip(groups, layout):
@@ -49,6 +50,83 @@ class FusedAdamW:
                 o += k
             self.param_groups.append({"params": ps, "lr": g.get("lr", lr), "weight_decay": g.get("weight_decay", weight_decay),
                                       "name": g.get("name", ""), "_off": off, "_n": n_pad})
+
+    # ------------------------------------------------------------------------------------ data parallel over NVLink peer memory
+    def enable_peer_step(self, group=None):
+        """Data-parallel step WITHOUT an all-reduce: parameters and gradients move into symmetric (peer-mapped) memory
+        (torch.distributed._symmetric_memory), every rank owns 1/world of each parameter group and one kernel per group
+        (psdf_adamw_dp_step, csrc/optim.cu) sums that shard of all ranks' gradients through NVLink peer loads, applies AdamW and
+        stores the new parameters into all ranks' buffers. Optimizer state is sharded (only the owner's moments are current;
+        state_dict() gathers them). Two device-side barriers bracket the kernels."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        grp = group if group is not None else dist.group.WORLD
+        world, rank = dist.get_world_size(grp), dist.get_rank(grp)
+        if world > 8:
+            raise RuntimeError("peer step supports up to 8 ranks of one NVLink domain")
+        dev = self.flat_param.device
+        total = self.flat_param.numel()
+        new_p = symm.empty(total, dtype=torch.float32, device=dev)
+        new_g = symm.empty(total, dtype=torch.float32, device=dev)
+        new_p.copy_(self.flat_param)
+        new_g.copy_(self.flat_grad)
+        hp, hg = symm.rendezvous(new_p, grp), symm.rendezvous(new_g, grp)
+        for g in self.param_groups:
+            o = g["_off"]
+            for p in g["params"]:
+                k = p.numel()
+                p.data = new_p[o:o + k].view_as(p)
+                p.grad = new_g[o:o + k].view_as(p)
+                o += k
+        self.flat_param, self.flat_grad = new_p, new_g
+        shards, gptrs, pptrs = [], [], []
+        for g in self.param_groups:
+            n4 = g["_n"] // 4
+            base, rem = divmod(n4, world)
+            lo4 = rank * base + min(rank, rem)
+            cnt4 = base + (1 if rank < rem else 0)
+            shards.append((lo4 * 4, cnt4 * 4))
+            gptrs.append(torch.tensor([int(hg.buffer_ptrs[r]) + 4 * g["_off"] for r in range(world)], dtype=torch.int64))
+            pptrs.append(torch.tensor([int(hp.buffer_ptrs[r]) + 4 * g["_off"] for r in range(world)], dtype=torch.int64))
+        import os
+        # NVSwitch multicast (in-switch reduction + replication) cuts the per-rank NVLink bytes from (W-1)/W to 1/W of the buffers: pays
+        # from 4 ranks on; at 2 ranks the unicast kernel is faster (measured on B200: 161 vs 241 us, tools/dp_step_timing.py)
+        want = os.environ.get("PSDF_DP_MULTICAST", "auto")
+        mc = (want == "1" or (want == "auto" and world >= 4)) and bool(getattr(hp, "has_multicast_support", False)) and \
+            int(hp.multicast_ptr) != 0 and int(hg.multicast_ptr) != 0
+        self._peer = dict(world=world, rank=rank, hp=hp, hg=hg, shards=shards, gptrs=gptrs, pptrs=pptrs, group=grp,
+                          mc_grad=int(hg.multicast_ptr) if mc else 0, mc_param=int(hp.multicast_ptr) if mc else 0, multicast=mc)
+        torch.cuda.synchronize()
+        dist.barrier(group=grp)
+
+    def _peer_step(self, grad_scale, advance):
+        pe = self._peer
+        if advance:
+            self.step_count += 1
+        b1, b2 = self.betas
+        step_dev = None
+        if self.device_step:
+            if self.step_dev is None:
+                self.step_dev = torch.full((1,), self.step_count - 1, dtype=torch.int32, device=self.flat_param.device)
+            if advance:
+                self.step_dev.add_(1)
+            step_dev = self.step_dev
+            if self.hyper_dev is None:
+                self.sync_hyper()
+        pe["hg"].barrier(channel=0)                  # every rank's backward has finished: all gradient buffers are final
+        for gi, g in enumerate(self.param_groups):
+            off, n = g["_off"], g["_n"]
+            lo, cnt = pe["shards"][gi]
+            if cnt == 0:
+                continue
+            hyper = self.hyper_dev[gi] if self.device_step else None
+            call("psdf_adamw_dp_step", cnt, lo, pe["world"], pe["rank"], pe["gptrs"][gi].data_ptr(), pe["pptrs"][gi].data_ptr(),
+                 pe["mc_grad"] + 4 * off if pe["multicast"] else 0, pe["mc_param"] + 4 * off if pe["multicast"] else 0,
+                 self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n], float(g["lr"]), b1, b2, self.eps, float(g["weight_decay"]),
+                 self.step_count, step_dev, hyper, float(grad_scale))
+        pe["hp"].barrier(channel=0)                  # every owner has written its shard into every rank's parameters
+        self.flat_grad.zero_()                       # ... and has read this rank's gradients
+        self._clean = True
 
     def zero_grad(self, set_to_none=False):
         # the step kernel zeroes the gradients it consumed; a backward that was not followed by a step leaves them dirty
@@ -79,20 +157,26 @@ class FusedAdamW:
             self._hyper_cached = cur
 
     @torch.no_grad()
-    def step(self, grad_scale=1.0):
-        self.step_count += 1
+    def step(self, grad_scale=1.0, groups=None, advance=True):
+        """groups: indices of the param groups to sweep (None: all). advance=False: a second call of the same optimizer step (the
+        data-parallel path steps the colour hash table while the other gradients are still being all-reduced)."""
+        if self._peer is not None:
+            return self._peer_step(grad_scale, advance)
+        if advance:
+            self.step_count += 1
         b1, b2 = self.betas
         step_dev = None
         if self.device_step:            # CUDA-graph mode: the step counter lives (and is incremented) on the device
             if self.step_dev is None:
                 self.step_dev = torch.full((1,), self.step_count - 1, dtype=torch.int32, device=self.flat_param.device)
-            self.step_dev.add_(1)
+            if advance:
+                self.step_dev.add_(1)
             step_dev = self.step_dev
             if self.hyper_dev is None:
                 self.sync_hyper()
         for gi, g in enumerate(self.param_groups):
             off, n = g["_off"], g["_n"]
-            if n == 0:
+            if n == 0 or (groups is not None and gi not in groups):
                 continue
             hyper = self.hyper_dev[gi] if self.device_step else None
             call("psdf_adamw_step", n, self.flat_param[off:off + n], self.flat_grad[off:off + n], self.exp_avg[off:off + n],
@@ -100,7 +184,21 @@ class FusedAdamW:
                  hyper, float(grad_scale), 1)
         self._clean = True
 
+    def _gather_peer_state(self):
+        """sharded moments -> full (every rank): zero what this rank does not own, sum over the ranks"""
+        import torch.distributed as dist
+        pe = self._peer
+        for t in (self.exp_avg, self.exp_avg_sq):
+            keep = torch.zeros_like(t)
+            for g, (lo, cnt) in zip(self.param_groups, pe["shards"]):
+                a = g["_off"] + lo
+                keep[a:a + cnt] = t[a:a + cnt]
+            dist.all_reduce(keep, group=pe["group"])
+            t.copy_(keep)
+
     def state_dict(self):
+        if self._peer is not None:
+            self._gather_peer_state()
         return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
                 "groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]}
 

@@ -53,6 +53,8 @@ class HyperParams:
     use_lr_schedule = True           # GradualWarmupScheduler(multiplier=1, total_epoch=3000) -> MultiStepLR(gamma=0.3)
     eikonal_weight_late = 0.01       # eikonal weight once iter >= iter_start_reduce_curv (:405)
     rgb_encoding_wd_late = 1.0       # weight decay of model_rgb_only_encoding from the same iteration on (:400-403)
+    jitter_samples = None            # None: jitter while training (reference behaviour); True / False force it (tests)
+    dp_world = 1                     # data-parallel ranks (set by Trainer.enable_data_parallel): sample-count weighting of the per-sample means
     adaptive_nr_rays = False         # nr_rays_to_create *= target_nr_of_samples / cur_nr_samples (:395-397); needs a host read per iteration
     nr_rays_bucket = 64              # adaptive ray counts are rounded to this multiple (bounded set of shapes / captured graphs)
 
@@ -87,11 +89,11 @@ def create_samples(with_mask, hyperparams, ray_origins, ray_dirs, jitter_samples
     return fg, bg
 
 
-# sphere_trace's loop as one tcgen05 kernel instead of ~12 launches + a sync per iteration. Measured on B200 (tools/bench_sphere_trace.py,
-# profiles/README.md): 3x faster than the masked loop at 256x256 rays (4.2 vs 13.2 ms), 2.8x slower at 1920x1080 (67 vs 24 ms) where
-# the loop's per-iteration compaction and its massively parallel occupancy marches win; crossover ~150 k rays.
+# sphere_trace's loop as one tcgen05 kernel instead of ~12 launches + a host sync per iteration (csrc/fused_sdf.cu k_sdf_sphere_trace:
+# persistent CTAs over a global ray queue, finished slots refilled, resumable marches). Measured on B200 at 1920x1080, 256 iterations
+# max (profiles/README.md): 10 ms for the trace against 136 ms for the masked loop; it wins at every frame size, so there is no ray limit.
 FUSED_SPHERE_TRACE = True
-FUSED_SPHERE_TRACE_MAX_RAYS = 131072
+FUSED_SPHERE_TRACE_MAX_RAYS = 1 << 30
 FUSED_IMPORTANCE_ROUND = True     # one launch per round (csrc/volrender.cu k_importance_round) instead of 9
 
 
@@ -107,16 +109,17 @@ def _imp_round(rsp, sdf, inv_s, inv_s_multiplier, ray_origins, ray_dirs, nr_imp,
     return VolumeRendering.importance_sample(ray_origins, ray_dirs, rsp, cdf, nr_imp, jitter)
 
 
-def importance_sampling_sdf_model(model_sdf, rsp, ray_origins, ray_dirs, ray_t_exit, iter_nr_for_anneal, nr_imp=16):
+def importance_sampling_sdf_model(model_sdf, rsp, ray_origins, ray_dirs, ray_t_exit, iter_nr_for_anneal, nr_imp=16, jitter=None):
     inv_s_imp_sampling = 512
+    jitter = model_sdf.training if jitter is None else bool(jitter)
     sdf, _ = model_sdf(rsp.samples_pos, iter_nr_for_anneal)
     rsp.set_sdf(sdf)
-    imp = _imp_round(rsp, sdf, inv_s_imp_sampling, 1.0, ray_origins, ray_dirs, nr_imp, model_sdf.training)
+    imp = _imp_round(rsp, sdf, inv_s_imp_sampling, 1.0, ray_origins, ray_dirs, nr_imp, jitter)
     sdf_imp, _ = model_sdf(imp.samples_pos, iter_nr_for_anneal)
     imp.set_sdf(sdf_imp)
     rsp = VolumeRendering.combine_uniform_samples_with_imp(ray_origins, ray_dirs, ray_t_exit, rsp, imp).compact_to_valid_samples()
     # second round: sharper density, reuse the merged sdf (no network evaluation)
-    imp = _imp_round(rsp, rsp.samples_sdf, inv_s_imp_sampling, 2.0, ray_origins, ray_dirs, nr_imp, model_sdf.training)
+    imp = _imp_round(rsp, rsp.samples_sdf, inv_s_imp_sampling, 2.0, ray_origins, ray_dirs, nr_imp, jitter)
     rsp.remove_sdf()
     rsp = VolumeRendering.combine_uniform_samples_with_imp(ray_origins, ray_dirs, ray_t_exit, rsp, imp).compact_to_valid_samples()
     return rsp
@@ -128,11 +131,19 @@ def run_net(with_mask, hyperparams, ray_origins, ray_dirs, img_indices, model_sd
     rgb / mask / eikonal losses run in the fused kernel pair (csrc/neus_fused.cu); the result lands in fused_loss['loss']."""
     with torch.no_grad():
         _, _, _, ray_t_exit, _ = model_sdf.boundary_primitive.ray_intersection(ray_origins, ray_dirs)
-        fg, bg = create_samples(with_mask, hyperparams, ray_origins, ray_dirs, model_sdf.training, occupancy_grid,
+        jitter = model_sdf.training if getattr(hyperparams, "jitter_samples", None) is None else bool(hyperparams.jitter_samples)
+        fg, bg = create_samples(with_mask, hyperparams, ray_origins, ray_dirs, jitter, occupancy_grid,
                                 model_sdf.boundary_primitive)
         if hyperparams.do_importance_sampling and fg.samples_pos.shape[0] != 0:
             fg = importance_sampling_sdf_model(model_sdf, fg, ray_origins, ray_dirs, ray_t_exit, iter_nr_for_anneal,
-                                               hyperparams.nr_samples_imp_sampling)
+                                               hyperparams.nr_samples_imp_sampling, jitter=jitter)
+        if getattr(hyperparams, "dp_world", 1) > 1:
+            # per-sample means (eikonal, curvature) are means over the samples of all ranks: one 4-byte all-reduce of the count
+            import torch.distributed as dist
+            n_sum = fg.cur_nr_samples.to(torch.int32).clone()
+            dist.all_reduce(n_sum, op=dist.ReduceOp.SUM)
+            W = int(hyperparams.dp_world)
+            fg.dp_mean_nr_samples = torch.div(n_sum + W // 2, W, rounding_mode="floor").to(torch.int32).clamp(min=1)
     if fg.samples_pos.shape[0] == 0:
         pred_rgb = torch.zeros_like(ray_origins)
         pred_normals = torch.zeros_like(ray_origins)
@@ -351,6 +362,7 @@ class Trainer:
             self.optimizer = torch.optim.AdamW(groups, amsgrad=False, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, lr=hp.lr)
         self.iter_nr = 0
         self._cg = None                 # CUDA-graph state (enable_cuda_graph)
+        self._dp = None                 # data-parallel state (enable_data_parallel)
         self.nr_rays_to_create = hp.nr_rays
         self.last = {}
 
@@ -425,6 +437,8 @@ class Trainer:
             if self.fused_render:
                 loss_curv = self.model_sdf.curvature_loss(fg.samples_pos, sdf_gradients, iter_nr_for_anneal,
                                                           fg.cur_nr_samples if RaySamplesPacked.static_capacity else None)
+                if getattr(fg, "dp_mean_nr_samples", None) is not None:       # mean over the samples of all ranks (see run_net)
+                    loss_curv = loss_curv * (fg.cur_nr_samples.float() / fg.dp_mean_nr_samples.float()).squeeze(0)
             else:
                 _, curv = self.model_sdf.get_sdf_and_curvature_1d_precomputed_gradient_normal_based(fg.samples_pos, sdf_gradients,
                                                                                                     iter_nr_for_anneal)
@@ -447,6 +461,94 @@ class Trainer:
         self.last = dict(loss_rgb=loss_rgb.detach(), loss_eikonal=loss_eik.detach(), loss_curvature=loss_curv.detach(),
                          nr_samples=fg.samples_pos.shape[0], nr_samples_dev=fg.cur_nr_samples, fg=fg)
         return loss
+
+    # ------------------------------------------------------------------------------------ data parallel
+    def enable_data_parallel(self, world, overlap=False, mode="peer"):
+        """Rays are sharded by rank, parameters replicated (same seed), gradients summed over the ranks and the mean folded into AdamW.
+        The flat gradient buffer is reduced in buckets that overlap with compute instead of one blocking all-reduce between backward
+        and optimizer:
+          * the colour hash table's gradient (half of the bytes) is final as soon as the colour network's backward kernel has run --
+            it runs FIRST in loss.backward() -- so its all-reduce is started right there and travels over NVLink while the SDF
+            backward kernels run;
+          * the rest is reduced after the backward while AdamW already sweeps the (reduced) colour hash table.
+        Per-sample means (eikonal, curvature) are weighted by the sample counts of all ranks (run_net), so the averaged gradient is the
+        gradient of the global batch. Works eagerly and inside the captured graphs (NCCL collectives are capturable)."""
+        import torch.distributed as dist
+        if not hasattr(self.optimizer, "flat_grad"):
+            raise RuntimeError("data-parallel mode needs the flat-buffer optimizer (optimizer='fused')")
+        self.hp.dp_world = int(world)
+        if mode == "peer":
+            # no all-reduce at all: one fused reduce + AdamW + broadcast kernel per parameter group over NVLink peer memory
+            # (optim.FusedAdamW.enable_peer_step, csrc/optim.cu k_adamw_dp); the step runs eagerly behind the replayed iteration graph
+            self.optimizer.enable_peer_step()
+            self._dp = dict(world=int(world), mode="peer", work=None, dist=dist)
+            if getattr(self.model_sdf, "fused", None) is not None:
+                self.model_sdf.fused.repack()
+            if self._cg is not None:
+                self._cg["fb"], self._cg["opt"] = None, {}      # captured graphs point at the old buffers
+            return
+        gi = next(i for i, g in enumerate(self.optimizer.param_groups) if g.get("name") == "model_rgb_only_encoding")
+        g = self.optimizer.param_groups[gi]
+        self._dp = dict(world=int(world), mode="nccl", rgb_group=gi, off=g["_off"], n=g["_n"], overlap=bool(overlap), work=None, dist=dist)
+        if overlap and getattr(self.model_rgb, "fused", None) is not None:
+            self.model_rgb.fused.after_backward = self._dp_start_rgb_table_reduce
+        if self._cg is not None:
+            self._cg["fb"], self._cg["opt"] = None, {}      # graphs captured without the collectives are stale
+
+    def _dp_start_rgb_table_reduce(self):
+        dp = self._dp
+        fg = self.optimizer.flat_grad
+        dp["work"] = dp["dist"].all_reduce(fg[dp["off"]:dp["off"] + dp["n"]], op=dp["dist"].ReduceOp.SUM, async_op=True)
+
+    def _dp_join_backward(self):
+        """end of the backward: the early bucket's collective rejoins the stream (needed before a graph capture ends); if the colour
+        network did not start it (modular path), nothing is pending"""
+        dp = getattr(self, "_dp", None)
+        if dp is not None and dp["work"] is not None:
+            dp["work"].wait()
+            dp["work"] = None
+            dp["rgb_reduced"] = True
+
+    def dp_reduce_gradients(self):
+        """finish the data-parallel reduction WITHOUT stepping (tests / inspection): flat_grad <- mean over the ranks"""
+        dp = self._dp
+        dist, fg = dp["dist"], self.optimizer.flat_grad
+        if dp["mode"] == "peer":
+            dist.all_reduce(fg, op=dist.ReduceOp.SUM)
+            fg.mul_(1.0 / dp["world"])
+            return
+        lo, hi = dp["off"], dp["off"] + dp["n"]
+        if dp.pop("rgb_reduced", False):
+            if lo > 0:
+                dist.all_reduce(fg[:lo], op=dist.ReduceOp.SUM)
+            if hi < fg.numel():
+                dist.all_reduce(fg[hi:], op=dist.ReduceOp.SUM)
+        else:
+            dist.all_reduce(fg, op=dist.ReduceOp.SUM)
+        fg.mul_(1.0 / dp["world"])
+
+    def _dp_optimizer_step(self, rgb_reduced):
+        """all-reduce of what is not reduced yet, overlapped with AdamW on the colour hash table; mean folded into the step"""
+        dp = self._dp
+        dist, fg, opt = dp["dist"], self.optimizer.flat_grad, self.optimizer
+        scale = 1.0 / dp["world"]
+        if dp["mode"] == "peer":
+            opt.step(grad_scale=scale)
+            return
+        lo, hi = dp["off"], dp["off"] + dp["n"]
+        if rgb_reduced:
+            works = []
+            if lo > 0:
+                works.append(dist.all_reduce(fg[:lo], op=dist.ReduceOp.SUM, async_op=True))
+            if hi < fg.numel():
+                works.append(dist.all_reduce(fg[hi:], op=dist.ReduceOp.SUM, async_op=True))
+            opt.step(grad_scale=scale, groups=[dp["rgb_group"]])
+            for w in works:
+                w.wait()
+            opt.step(grad_scale=scale, groups=[i for i in range(len(opt.param_groups)) if i != dp["rgb_group"]], advance=False)
+        else:
+            dist.all_reduce(fg, op=dist.ReduceOp.SUM)
+            opt.step(grad_scale=scale)
 
     def apply_schedules(self, it):
         """host-side schedule edits of one iteration, run between the loss and the optimizer step like the reference does
@@ -497,6 +599,7 @@ class Trainer:
         self.apply_schedules(it)
         self.optimizer.zero_grad(set_to_none=False)
         loss.backward()
+        self._dp_join_backward()
         if optimizer_step:
             self.optimizer_step()
         self.iter_nr += 1
@@ -518,7 +621,7 @@ class Trainer:
         dev = opt.flat_param.device
         opt.step_dev = torch.full((1,), opt.step_count, dtype=torch.int32, device=dev)
         opt.sync_hyper()
-        self._cg = dict(warm=int(warmup_steps), fb=None, opt={}, it_dev=torch.zeros((), device=dev), it_host=None,
+        self._cg = dict(warm=int(warmup_steps), fb=None, opt={}, occ=None, it_dev=torch.zeros((), device=dev), it_host=None,
                         stream=torch.cuda.Stream(device=dev), launches=0)
 
     def disable_cuda_graph(self):
@@ -578,6 +681,7 @@ class Trainer:
                 loss = self.losses(*args, DeviceIter(it, cg["it_dev"]))
                 self.optimizer.zero_grad(set_to_none=False)
                 loss.backward()
+                self._dp_join_backward()
                 loss = loss.detach()
             cur.wait_stream(side)
         else:
@@ -596,7 +700,7 @@ class Trainer:
         if update_occupancy is None:
             update_occupancy = (it % 8 == 0)
         if update_occupancy and self.hp.use_occupancy_grid:
-            self.update_occupancy(it)
+            self._update_occupancy_graphed(it)
         if self.hp.adaptive_nr_rays:
             self.adapt_nr_rays(int(self.last["nr_samples_dev"].item()))     # the reference's loop reads the count every iteration too
         self.apply_schedules(it)
@@ -604,6 +708,28 @@ class Trainer:
             self.optimizer_step()
         self.iter_nr += 1
         return loss
+
+    def _update_occupancy_graphed(self, it):
+        """the occupancy refresh of every 8th iteration (random voxel sample -> fused SDF forward -> grid update,
+        train_permuto_sdf.py:386-391) as a third replayed graph: one launch instead of five, same device-resident schedule rule
+        (re-captured when the iteration leaves the range for which the captured branches hold)"""
+        cg = self._cg
+        og = cg.get("occ")
+        if cg["fb"] is None:                     # warm-up iterations: eager, on the capture stream
+            side, cur = cg["stream"], torch.cuda.current_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self.update_occupancy(DeviceIter(it, cg["it_dev"]))
+            cur.wait_stream(side)
+            return
+        if og is None or not (og["lo"] <= it < og["hi"]):
+            dit = DeviceIter(it, cg["it_dev"])
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=cg["stream"]):
+                self.update_occupancy(dit)
+            og = cg["occ"] = dict(graph=g, lo=dit.lo, hi=dit.hi)
+        og["graph"].replay()
 
     def _capture_forward_backward(self, inputs, shapes, it, make_rays=None):
         cg = self._cg
@@ -621,43 +747,59 @@ class Trainer:
                     args = make_rays(*static)
             loss = self.losses(*args, dit)
             loss.backward()
+            self._dp_join_backward()
             out = loss.detach()
         _, launches, _ = stats_end()
-        return dict(graph=g, static=static, loss=out, last=self.last, shapes=shapes, lo=dit.lo, hi=dit.hi, launches=launches)
+        dp_rgb = bool(self._dp.pop("rgb_reduced", False)) if getattr(self, "_dp", None) is not None else False
+        cg["occ"] = None               # the refresh graph reads tensors of the iteration graph (last inv_s): capture it again
+        return dict(graph=g, static=static, loss=out, last=self.last, shapes=shapes, lo=dit.lo, hi=dit.hi, launches=launches,
+                    dp_rgb_reduced=dp_rgb)
 
     def _optimizer_step_graphed(self, grad_scale, allreduce=False):
-        """allreduce=True: the data-parallel sum of the flat gradient buffer (NCCL) is part of the step -- captured in the optimizer
-        graph, so that a replayed iteration is two graph launches and nothing else"""
+        """the optimizer half of a replayed iteration: (data-parallel: bucketed all-reduce overlapped with AdamW,) AdamW, weight re-pack,
+        iteration++ -- captured once per (grad_scale, collective layout) and replayed; NCCL collectives are part of the graph"""
         cg = self._cg
-        if allreduce:
-            import torch.distributed as dist
+        dp = getattr(self, "_dp", None)
         self.optimizer.sync_hyper()     # lr / weight_decay edits since the last replay -> device (outside any capture)
+        if dp is not None:
+            rgb_done = cg["fb"]["dp_rgb_reduced"] if cg["fb"] is not None else dp.pop("rgb_reduced", False)
+        else:
+            rgb_done = False
+
+        def work():
+            if dp is not None:
+                self._dp_optimizer_step(rgb_done)
+            else:
+                if allreduce:
+                    import torch.distributed as dist
+                    dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
+                self.optimizer.step(grad_scale=grad_scale)
+            self.model_sdf.fused.repack()
+            cg["it_dev"].add_(1.0)
+
         if cg["fb"] is None:            # still in the eager warm-up iterations
             side, cur = cg["stream"], torch.cuda.current_stream()
             side.wait_stream(cur)
             with torch.cuda.stream(side):
-                if allreduce:
-                    dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
-                self.optimizer.step(grad_scale=grad_scale)
-                self.model_sdf.fused.repack()
-                cg["it_dev"].add_(1.0)
+                work()
             cur.wait_stream(side)
+        elif dp is not None and dp["mode"] == "peer":
+            # the cross-rank barriers of the peer-memory step are launched eagerly, right behind the replayed iteration graph (a handful
+            # of launches; the host is far ahead of the GPU)
+            work()
         else:
-            og = cg["opt"].get((grad_scale, allreduce))
+            key = (grad_scale, allreduce, dp is not None, rgb_done)
+            og = cg["opt"].get(key)
             if og is None:
                 from ._lib import stats_begin, stats_end
                 torch.cuda.synchronize()
                 stats_begin(with_events=False)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=cg["stream"]):
-                    if allreduce:
-                        dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
-                    self.optimizer.step(grad_scale=grad_scale)
-                    self.model_sdf.fused.repack()
-                    cg["it_dev"].add_(1.0)
+                    work()
                 _, launches, _ = stats_end()
                 self.optimizer.step_count -= 1          # capture records, it does not run
-                og = cg["opt"][(grad_scale, allreduce)] = dict(graph=g, launches=launches)
+                og = cg["opt"][key] = dict(graph=g, launches=launches)
             og["graph"].replay()
             self.optimizer.step_count += 1
         if cg["it_host"] is not None:
@@ -671,8 +813,15 @@ class Trainer:
         return cg["fb"]["launches"] + sum(o["launches"] for o in cg["opt"].values())
 
     def optimizer_step(self, grad_scale=1.0, allreduce=False):
+        """AdamW (+ weight re-pack). After enable_data_parallel() the gradient all-reduce and the 1/world mean are part of the step."""
         if self._cg is not None:
             return self._optimizer_step_graphed(float(grad_scale), bool(allreduce))
+        dp = getattr(self, "_dp", None)
+        if dp is not None:
+            self._dp_optimizer_step(dp.pop("rgb_reduced", False))
+            if getattr(self.model_sdf, "fused", None) is not None:
+                self.model_sdf.fused.repack()
+            return
         if allreduce:
             import torch.distributed as dist
             dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)

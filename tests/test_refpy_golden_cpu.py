@@ -44,3 +44,38 @@ def test_fixture_regenerates_from_the_reference(tmp_path):
             assert np.allclose(a[k], b[k], rtol=1e-5, atol=1e-7), k
         else:
             assert np.array_equal(a[k], b[k]), k
+
+
+_PATCH_CHECK = r"""
+import sys, torch
+sys.path.insert(0, %r)
+from oracle import refpy
+M = refpy.install()
+import permuto_sdf as ps
+import permuto_sdf_b200
+torch.manual_seed(0)
+sdf = M.SDF(in_channels=3, boundary_primitive=ps.Sphere(0.5, [0, 0, 0]), geom_feat_size_out=32, nr_iters_for_c2f=10000)
+with torch.no_grad():
+    sdf.encoding.lattice_values.uniform_(-0.3, 0.3)
+pts = (torch.rand(64, 3) - 0.5) * 0.8
+a = sdf.get_sdf_and_gradient(pts.clone(), 3000)
+orig_forward = M.SDF.forward
+permuto_sdf_b200.patch_reference_models(M)
+assert M.SDF.forward is not orig_forward and hasattr(M.SDF, "enable_fused_training") and hasattr(M.RGB, "enable_fused")
+b = sdf.get_sdf_and_gradient(pts.clone(), 3000)           # CPU tensors: the grafted methods take the per-op branch (no fused path on CPU)
+assert sdf.fused is None
+for x, y in zip(a, b):
+    assert torch.allclose(x, y, rtol=1e-6, atol=1e-7)
+assert list(sdf.state_dict().keys()) == ["encoding.lattice_values", "encoding.random_shift_per_level"] + ["mlp_sdf.%%d.%%s" %% (i, n) for i in (0, 2, 4, 6) for n in ("weight", "bias")]
+permuto_sdf_b200.unpatch_reference_models(M)
+assert M.SDF.forward is orig_forward
+print("PATCH-OK")
+"""
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/permuto_sdf_py"), reason="the reference's Python exists only in the build container")
+def test_patch_grafts_onto_the_real_reference_classes():
+    """permuto_sdf_b200.patch_reference_models on the UNMODIFIED permuto_sdf_py/models/models.py (own process: oracle/refpy.py replaces
+    sys.modules entries): methods replaced, instances keep parameters / state_dict keys / results, unpatch restores"""
+    r = subprocess.run([sys.executable, "-c", _PATCH_CHECK % ROOT], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PATCH-OK" in r.stdout, r.stderr[-3000:]
