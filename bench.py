@@ -46,25 +46,52 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
+    """SM clock / throttle reasons during the timed region. NVML is polled every ~2 ms from a thread (a 34 ms timed region gets ~15
+    samples); falls back to nvidia-smi (one sample per ~0.2 s) when the NVML binding is not importable."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
         self.index, self.rows, self.stop, self.th = index, [], False, None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
-    def _run(self):
+    def _run_nvml(self):
+        n = self.nvml
+        R = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self.stop:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+                r = int(R(self.h))
+                self.rows.append((sm, self.max_sm, [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _run_smi(self):
         while not self.stop:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                    c = [t.strip() for t in out.split(",")]
+                    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                    self.rows.append((float(c[0]), float(c[1]), [nm for i, nm in enumerate(names) if c[2 + i].lower().startswith("active")]))
             except Exception:
                 pass
             time.sleep(0.2)
 
     def __enter__(self):
-        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th = threading.Thread(target=self._run_nvml if self.nvml is not None else self._run_smi, daemon=True)
         self.th.start()
         return self
 
@@ -75,11 +102,10 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows if len(r) > 2 + i)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.rows)}
+        sm = [r[0] for r in self.rows]
+        reasons = sorted({x for r in self.rows for x in r[2]})
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(r[1] for r in self.rows), "reasons": reasons, "samples": len(self.rows),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def analytic_reel(nimg, H, W, f, device):
@@ -193,6 +219,8 @@ def run_ours(args):
             one_step(i % total, False)
         torch.cuda.synchronize()
 
+    static_eager = False
+
     def timed(e2e, with_events, steps=None):
         steps = args.steps if steps is None else steps
         for i in range(args.warmup):
@@ -211,7 +239,7 @@ def run_ours(args):
                 e.record()
                 evs.append((s, e))
                 if not graphed:
-                    nsamples += tr.last["nr_samples"]
+                    nsamples += int(tr.last["nr_samples_dev"]) if static_eager else tr.last["nr_samples"]
             torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -229,10 +257,11 @@ def run_ours(args):
     if graphed:
         # kernels inside the replayed graphs (counted at capture) + the eager calls of the timed region (occupancy refresh)
         launches += tr.graph_launches_per_step() * args.steps
-        # per-kernel CUDA-event times and the sample count come from a few eager iterations of the same workload afterwards
-        # (events cannot bracket individual kernels of a replayed graph); outside the timed region
-        tr.disable_cuda_graph()
-        graphed = False
+        # per-kernel CUDA-event times and the sample count come from a few iterations of the same workload afterwards, outside the
+        # timed region (events cannot bracket individual kernels of a replayed graph): same static-capacity containers and
+        # device-resident generators / schedule as under replay, but every kernel launched from Python
+        tr._cg["fb"], tr._cg["opt"], tr._cg["occ"], tr._cg["warm"] = None, {}, None, 1 << 30
+        graphed, static_eager = False, True
         prof_steps = min(args.steps, 5)
         ms_prof, _, ktimes, _, avg_samples = timed(e2e=False, with_events=True, steps=prof_steps)
         sc = args.steps / prof_steps                                  # rescale to the timed region's step count
@@ -269,7 +298,8 @@ def run_ours(args):
                 "traffic": ncu_traffic.get(name), "launches": n, "avg_us": per_launch_s * 1e6, "samples_per_launch": nsamp / n if n else None,
                 "peak_source": peak_src,
                 "share_of_step": tot_ms / ms_dev,
-                "top5_ms_per_step": {k: round(v / args.steps, 4) for v, k in top[:5]}}
+                "top5_ms_per_step": {k: round(v / args.steps, 4) for v, k in top[:5]},
+                "calls_per_step": {k: round(ktimes[k][0] / args.steps, 2) for _, k in top[:12]}}
 
     out = None
     if rank == 0:
@@ -413,8 +443,9 @@ def run_sphere_trace(args):
                           "timed_region": "sum of per-frame CUDA-event intervals"},
                "e2e": {"value": px / (ms_e2e / 1e3), "unit": "px/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 24 * world,
                        "d2h_bytes_per_step": W * H * 3 * 4},
-               "gpu_launches": launches, "clocks": clocks, "roofline": roof,
-               "cpu_baseline": cpu_baseline(sample_rays=8, steps=3, warmup=1)}
+               "gpu_launches": launches, "clocks": clocks, "roofline": roof}
+        with torch.enable_grad():
+            out["cpu_baseline"] = cpu_baseline(sample_rays=8, steps=3, warmup=1)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

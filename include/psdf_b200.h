@@ -269,6 +269,16 @@ int psdf_rgb_fused_forward(int N, int L, int T, const float* pos, const float* d
 /* backward of psdf_rgb_fused_forward: g_out [N,3] = d loss / d out -> grad_lattice (+=), g_sdf_grad [N,3] (=), g_geom [N,32] (=),
  * weight gradients gW_l [N_l,K_l] (+=, wrt the normalised matrices) and bias gradients gb_l (+=). workspace:
  * psdf_rgb_fused_backward_workspace_bytes(N) bytes of scratch. */
+/* psdf_sdf_fused_backward over up to three independent sample sets in ONE launch (N_i = 0: unused set); every set has its own
+ * positions and upstream gradients, the accumulated parameter gradients are shared. One launch of 1024 tiles loses 1 % to the last
+ * partial wave on 148 SMs where two launches of 512 tiles lose 13 % each. */
+long long psdf_sdf_fused_backward_multi_workspace_bytes(int N0, int N1, int N2);
+int psdf_sdf_fused_backward_multi(int L, int T, const float* lattice, const float* scale_factor, const float* shift, const float* window,
+                                  float points_scaling, int hidden, int out_dim, const uint8_t* blob, int N0, const float* pos0,
+                                  const float* g_sdf0, const float* g_grad0, const float* g_geom0, int N1, const float* pos1,
+                                  const float* g_sdf1, const float* g_grad1, const float* g_geom1, int N2, const float* pos2,
+                                  const float* g_sdf2, const float* g_grad2, const float* g_geom2, float* grad_lattice, uint8_t* workspace,
+                                  float* gW0, float* gW1, float* gW2, float* gW3, float* gb0, float* gb1, float* gb2, float* gb3, void* stream);
 long long psdf_rgb_fused_backward_workspace_bytes(int N);
 int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
                             const float* lattice, const float* scale_factor, const float* shift, const float* window, float points_scaling,

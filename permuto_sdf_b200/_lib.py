@@ -187,6 +187,24 @@ def stats_begin(with_events=False):
     _STATS = {"calls": {}, "events": {} if with_events else None}
 
 
+def stats_pause():
+    """suspend the current statistics window (a nested window may run in between); -> token for stats_resume"""
+    global _STATS
+    st, _STATS = _STATS, None
+    return st
+
+
+def stats_resume(token):
+    global _STATS
+    _STATS = token
+
+
+def stats_add_launches(n):
+    """kernels of this library launched outside `call` (a replayed graph) inside the current window"""
+    if _STATS is not None:
+        _STATS["extra"] = _STATS.get("extra", 0) + int(n)
+
+
 def stats_end():
     """-> (calls per entry point, kernel launches, {name: (n, total_ms)} if events were recorded)"""
     global _STATS

@@ -52,6 +52,18 @@ struct BwdOut {
     float* gbias[kNL];  // [N_l]      (+=)
     unsigned long long* phase_cycles;   // [16] += clock64 deltas of thread 0 per phase (PSDF_PHASE_TIMING=1, diagnostics), else NULL
 };
+// Up to kMaxSeg independent sample sets (the main samples, the curvature pass' shifted samples, the off-surface points of one training
+// iteration) are processed by ONE launch: every set starts on a tile boundary; 1024 tiles on 148 SMs lose 1 % to the last partial wave
+// where two launches of 512 tiles lose 13 % each (3.46 -> 4 tile times per CTA).
+constexpr int kMaxSeg = 3;
+struct Segments {
+    int n[kMaxSeg];          // samples of the set
+    int tile0[kMaxSeg + 1];  // first tile of the set (prefix sum of ceil(n / 128))
+    const float* pos[kMaxSeg];
+    const float* g_sdf[kMaxSeg];
+    const float* g_grad[kMaxSeg];
+    const float* g_geom[kMaxSeg];
+};
 // phase ids of the diagnostic counters
 enum { kPhEncoder = 0, kPhForward = 1, kPhSeed = 2, kPhReverse3 = 3, kPhReverse2 = 4, kPhReverse1 = 5, kPhReverse0 = 6, kPhEncoderBwd = 7,
        kPhFlush = 8, kPhTiles = 9 };
@@ -149,9 +161,8 @@ __device__ __forceinline__ void issue_dw_part(uint32_t tmem_d, const uint8_t* zs
 }
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
-k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2* __restrict__ lattice, const float* __restrict__ scale,
+k_sdf_fused_backward(FusedParams P, Segments S, const float2* __restrict__ lattice, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ window, const uint8_t* __restrict__ blob,
-                     const float* __restrict__ g_sdf, const float* __restrict__ g_grad, const float* __restrict__ g_geom,
                      float* __restrict__ grad_lattice, BwdOut out) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* s_w = smem;                                   // forward operand blob (weights hi/lo + biases), resident
@@ -191,12 +202,17 @@ k_sdf_fused_backward(FusedParams P, const float* __restrict__ pos, const float2*
     umma::mbar_wait(&bars[0], 0);
     uint32_t ld_phase = 1, mma_phase = 0, dw_phase = 0;
 
-    const int ntiles = (P.N + kTile - 1) / kTile;
+    const int ntiles = S.tile0[kMaxSeg];
     bool first_tile = true;
     long long phase_t0 = out.phase_cycles ? clock64() : 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first_tile = false) {
-        const int n = tile * kTile + row;
-        const bool valid = n < P.N;
+        const int seg = tile >= S.tile0[2] ? 2 : (tile >= S.tile0[1] ? 1 : 0);
+        const int n = (tile - S.tile0[seg]) * kTile + row;           // row inside its sample set
+        const bool valid = n < S.n[seg];
+        const float* __restrict__ pos = S.pos[seg];
+        const float* __restrict__ g_sdf = S.g_sdf[seg];
+        const float* __restrict__ g_grad = S.g_grad[seg];
+        const float* __restrict__ g_geom = S.g_geom[seg];
         float x[3], v[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
@@ -519,24 +535,34 @@ long long psdf_sdf_fused_backward_workspace_bytes(int N) {
     return (long long)ntiles * kSetBytes;
 }
 
-// grad_lattice, grad_W_l [N_l, K_l] and grad_bias_l are accumulated (+=).
-int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
-                            const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, const float* g_sdf,
-                            const float* g_grad, const float* g_geom, float* grad_lattice, uint8_t* workspace, float* gW0, float* gW1,
-                            float* gW2, float* gW3, float* gb0, float* gb1, float* gb2, float* gb3, void* stream) {
-    if (N < 0 || L < 4 || L > kMaxLevels || (L % 4) != 0 || hidden > 64 || hidden % 16 != 0 || out_dim > 64) return PSDF_ERR_UNSUPPORTED;
-    if (N == 0) return PSDF_OK;
+static int launch_backward(int nseg, const int* Ns, const float* const* pos, const float* const* g_sdf, const float* const* g_grad,
+                           const float* const* g_geom, int L, int T, const float* lattice, const float* scale_factor, const float* shift,
+                           const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, float* grad_lattice,
+                           uint8_t* workspace, float* const* gW, float* const* gb, void* stream) {
+    if (nseg < 1 || nseg > kMaxSeg || L < 4 || L > kMaxLevels || (L % 4) != 0 || hidden > 64 || hidden % 16 != 0 || out_dim > 64) return PSDF_ERR_UNSUPPORTED;
     FusedParams P;
-    P.N = N; P.L = L; P.T = T;
+    P.L = L; P.T = T;
     P.cap_mask = t_magic(T);
     P.points_scaling = points_scaling;
     P.in_dim = (L + 2) * 2;
     if (P.in_dim > 64) return PSDF_ERR_UNSUPPORTED;
     P.g = make_geom(P.in_dim, hidden, out_dim);
+    Segments S;
+    int tiles = 0, total = 0;
+    for (int i = 0; i < kMaxSeg; i++) {
+        const int n = i < nseg ? Ns[i] : 0;
+        if (n < 0) return PSDF_ERR_ARG;
+        S.n[i] = n; S.tile0[i] = tiles;
+        S.pos[i] = i < nseg ? pos[i] : nullptr; S.g_sdf[i] = i < nseg ? g_sdf[i] : nullptr;
+        S.g_grad[i] = i < nseg ? g_grad[i] : nullptr; S.g_geom[i] = i < nseg ? g_geom[i] : nullptr;
+        tiles += div_up(n, kTile);
+        total += n;
+    }
+    S.tile0[kMaxSeg] = tiles;
+    P.N = total;
+    if (tiles == 0) return PSDF_OK;
     BwdOut out;
-    float* w[kNL] = {gW0, gW1, gW2, gW3};
-    float* b[kNL] = {gb0, gb1, gb2, gb3};
-    for (int l = 0; l < kNL; l++) { out.gW[l] = w[l]; out.gbias[l] = b[l]; }
+    for (int l = 0; l < kNL; l++) { out.gW[l] = gW[l]; out.gbias[l] = gb[l]; }
     out.a0_spill = workspace;
     // diagnostics: PSDF_PHASE_TIMING=1 prints thread 0's clock64 breakdown per phase (average cycles per tile) after every launch
     static const bool timing = getenv("PSDF_PHASE_TIMING") && atoi(getenv("PSDF_PHASE_TIMING")) != 0;
@@ -547,15 +573,14 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
         cudaMemsetAsync(d_cycles, 0, 16 * sizeof(unsigned long long), ST);
         out.phase_cycles = d_cycles;
     }
-    const int ntiles = div_up(N, kTile);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = (size_t)P.g.total + 2 * kSetBytes + sizeof(LevelC) + kNL * 64 * sizeof(float) + 64;
     if ((size_t)128 * (2 * P.g.Kp[0] + 1) * 4 > (size_t)2 * kSetBytes || smem > 227 * 1024) return PSDF_ERR_UNSUPPORTED;
     { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_fused_backward, 227 * 1024, optin_); }
-    k_sdf_fused_backward<<<min(ntiles, sms), kBwdThreads, smem, ST>>>(P, pos, reinterpret_cast<const float2*>(lattice), scale_factor, shift,
-                                                                      window, blob, g_sdf, g_grad, g_geom, grad_lattice, out);
+    k_sdf_fused_backward<<<min(tiles, sms), kBwdThreads, smem, ST>>>(P, S, reinterpret_cast<const float2*>(lattice), scale_factor, shift, window,
+                                                                    blob, grad_lattice, out);
     PSDF_CHECK_LAUNCH();
     if (timing) {
         unsigned long long h[16];
@@ -563,10 +588,48 @@ int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* 
         cudaStreamSynchronize(ST);
         const double t = h[kPhTiles] ? (double)h[kPhTiles] : 1.0;
         fprintf(stderr, "[psdf_sdf_fused_backward N=%d tiles=%llu] cycles/tile: encoder %.0f forward %.0f seed %.0f rev3 %.0f rev2 %.0f rev1 %.0f rev0 %.0f "
-                        "encoder_bwd %.0f | flush/CTA %.0f\n", N, h[kPhTiles], h[0] / t, h[1] / t, h[2] / t, h[3] / t, h[4] / t, h[5] / t, h[6] / t, h[7] / t,
-                (double)h[kPhFlush] / min(ntiles, sms));
+                        "encoder_bwd %.0f | flush/CTA %.0f\n", total, h[kPhTiles], h[0] / t, h[1] / t, h[2] / t, h[3] / t, h[4] / t, h[5] / t, h[6] / t, h[7] / t,
+                (double)h[kPhFlush] / min(tiles, sms));
     }
     return PSDF_OK;
+}
+
+// workspace of a multi-set launch: every set is padded to whole tiles
+long long psdf_sdf_fused_backward_multi_workspace_bytes(int N0, int N1, int N2) {
+    return (long long)(div_up(N0 > 0 ? N0 : 0, kTile) + div_up(N1 > 0 ? N1 : 0, kTile) + div_up(N2 > 0 ? N2 : 0, kTile) + 1) * kSetBytes;
+}
+
+// grad_lattice, grad_W_l [N_l, K_l] and grad_bias_l are accumulated (+=).
+int psdf_sdf_fused_backward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
+                            const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, const float* g_sdf,
+                            const float* g_grad, const float* g_geom, float* grad_lattice, uint8_t* workspace, float* gW0, float* gW1,
+                            float* gW2, float* gW3, float* gb0, float* gb1, float* gb2, float* gb3, void* stream) {
+    if (N < 0) return PSDF_ERR_ARG;
+    if (N == 0) return PSDF_OK;
+    float* gW[kNL] = {gW0, gW1, gW2, gW3};
+    float* gb[kNL] = {gb0, gb1, gb2, gb3};
+    return launch_backward(1, &N, &pos, &g_sdf, &g_grad, &g_geom, L, T, lattice, scale_factor, shift, window, points_scaling, hidden, out_dim, blob,
+                           grad_lattice, workspace, gW, gb, stream);
+}
+
+// The same backward over up to three independent sample sets in ONE launch (unused sets: N = 0). Used by the training iteration to run
+// the main samples, the curvature pass and the off-surface points together (each psdf_sdf_fused_forward call of the iteration has its
+// own upstream gradients; the parameters, hence the accumulated gradients, are shared).
+int psdf_sdf_fused_backward_multi(int L, int T, const float* lattice, const float* scale_factor, const float* shift, const float* window,
+                                  float points_scaling, int hidden, int out_dim, const uint8_t* blob, int N0, const float* pos0,
+                                  const float* g_sdf0, const float* g_grad0, const float* g_geom0, int N1, const float* pos1,
+                                  const float* g_sdf1, const float* g_grad1, const float* g_geom1, int N2, const float* pos2,
+                                  const float* g_sdf2, const float* g_grad2, const float* g_geom2, float* grad_lattice, uint8_t* workspace,
+                                  float* gW0, float* gW1, float* gW2, float* gW3, float* gb0, float* gb1, float* gb2, float* gb3, void* stream) {
+    const int Ns[3] = {N0, N1, N2};
+    const float* pos[3] = {pos0, pos1, pos2};
+    const float* gs[3] = {g_sdf0, g_sdf1, g_sdf2};
+    const float* gg[3] = {g_grad0, g_grad1, g_grad2};
+    const float* gm[3] = {g_geom0, g_geom1, g_geom2};
+    float* gW[kNL] = {gW0, gW1, gW2, gW3};
+    float* gb[kNL] = {gb0, gb1, gb2, gb3};
+    return launch_backward(3, Ns, pos, gs, gg, gm, L, T, lattice, scale_factor, shift, window, points_scaling, hidden, out_dim, blob, grad_lattice,
+                           workspace, gW, gb, stream);
 }
 
 }  // extern "C"

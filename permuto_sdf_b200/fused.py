@@ -62,6 +62,8 @@ class FusedSDF:
         self.blob = torch.empty(int(lib.psdf_sdf_mlp_blob_bytes(self.in_dim, self.hidden, self.out_dim)), dtype=torch.uint8,
                                 device=enc.lattice_values.device)
         self._versions = None
+        self._pending = []              # queued backward calls of the running autograd pass (batch_backward)
+        self.batch_backward = True      # with in-place gradients: one backward launch per iteration instead of one per forward call
         self.repack()
 
     def _cur_versions(self):
@@ -168,7 +170,6 @@ class _FusedSDFTrainFn(torch.autograd.Function):
         dev = points.device
         dims_k = [fused.in_dim, fused.hidden, fused.hidden, fused.hidden]
         dims_n = [fused.hidden, fused.hidden, fused.hidden, fused.out_dim]
-        ws = torch.empty(int(load_library().psdf_sdf_fused_backward_workspace_bytes(N)), dtype=torch.uint8, device=dev)
         # with a flat-buffer optimizer the gradients are accumulated straight into the persistent .grad buffers (hash table:
         # no 33 MB zero-fill plus accumulate pass per call; MLP: no zero-fills / add_ per tensor); autograd then gets no
         # gradient for those parameters from this node
@@ -182,13 +183,52 @@ class _FusedSDFTrainFn(torch.autograd.Function):
             gb = [torch.zeros(n, device=dev) for n in dims_n]
         g_lat = lattice.grad if in_place else torch.zeros_like(lattice)
         c = lambda t: None if t is None else t.contiguous()
-        # kernel 1: reverse sweep + lattice scatter + operand-tile spill; kernel 2: dW = zbar^T a on the tensor cores
+        if in_place and fused.batch_backward:
+            # gradients accumulate in the persistent .grad buffers and autograd gets nothing back from this node, so the launch can wait:
+            # every backward of this iteration (main samples, curvature pass, off-surface points) is queued and ONE kernel processes them
+            # all when the autograd pass has finished (engine callback) -- see psdf_sdf_fused_backward_multi
+            fused._queue_backward(points, c(g_sdf), c(g_grad), c(g_geom), window)
+            return (None,) * 12
+        ws = torch.empty(int(load_library().psdf_sdf_fused_backward_workspace_bytes(N)), dtype=torch.uint8, device=dev)
         call("psdf_sdf_fused_backward", N, enc.nr_levels, enc.capacity, points, lattice.detach(), enc.scale_factor, enc.shift_tensor(), window,
              enc.concat_points_scaling, fused.hidden, fused.out_dim, fused.blob, c(g_sdf), c(g_grad), c(g_geom), g_lat, ws, gW[0], gW[1], gW[2],
              gW[3], gb[0], gb[1], gb[2], gb[3])
         if in_place:
             return (None,) * 12
         return (None, g_lat, gW[0], gb[0], gW[1], gb[1], gW[2], gb[2], gW[3], gb[3], None, None)
+
+
+def _fused_sdf_queue_backward(self, points, g_sdf, g_grad, g_geom, window):
+    if not self._pending:
+        torch.autograd.Variable._execution_engine.queue_callback(self._flush_backward)
+    self._pending.append((points, g_sdf, g_grad, g_geom, window))
+
+
+def _fused_sdf_flush_backward(self):
+    """one launch per group of <= 3 queued sample sets that share the coarse-to-fine window"""
+    pend, self._pending = self._pending, []
+    enc = self.model.encoding
+    lattice = enc.lattice_values
+    lib = load_library()
+    while pend:
+        w0 = pend[0][4]
+        batch = [p for p in pend if p[4].data_ptr() == w0.data_ptr()][:3]
+        pend = [p for p in pend if not any(p is b for b in batch)]
+        batch.sort(key=lambda p: -p[0].shape[0])
+        segs = batch + [None] * (3 - len(batch))
+        ns = [0 if s is None else s[0].shape[0] for s in segs]
+        ws = torch.empty(int(lib.psdf_sdf_fused_backward_multi_workspace_bytes(*ns)), dtype=torch.uint8, device=lattice.device)
+        flat = []
+        for s, n in zip(segs, ns):
+            flat += [n] + ([None] * 4 if s is None else [s[0], s[1], s[2], s[3]])
+        call("psdf_sdf_fused_backward_multi", enc.nr_levels, enc.capacity, lattice.detach(), enc.scale_factor, enc.shift_tensor(), w0,
+             enc.concat_points_scaling, self.hidden, self.out_dim, self.blob, *flat, lattice.grad, ws,
+             self.lin[0].weight.grad, self.lin[1].weight.grad, self.lin[2].weight.grad, self.lin[3].weight.grad,
+             self.lin[0].bias.grad, self.lin[1].bias.grad, self.lin[2].bias.grad, self.lin[3].bias.grad)
+
+
+FusedSDF._queue_backward = _fused_sdf_queue_backward
+FusedSDF._flush_backward = _fused_sdf_flush_backward
 
 
 # ================================================================================================ NeuS compositing + losses

@@ -724,12 +724,20 @@ class Trainer:
             return
         if og is None or not (og["lo"] <= it < og["hi"]):
             dit = DeviceIter(it, cg["it_dev"])
+            from ._lib import stats_pause, stats_resume
             torch.cuda.synchronize()
+            paused = stats_pause()
+            from ._lib import stats_begin, stats_end
+            stats_begin(with_events=False)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=cg["stream"]):
                 self.update_occupancy(dit)
-            og = cg["occ"] = dict(graph=g, lo=dit.lo, hi=dit.hi)
+            _, launches, _ = stats_end()
+            stats_resume(paused)
+            og = cg["occ"] = dict(graph=g, lo=dit.lo, hi=dit.hi, launches=launches)
         og["graph"].replay()
+        from ._lib import stats_add_launches
+        stats_add_launches(og["launches"])
 
     def _capture_forward_backward(self, inputs, shapes, it, make_rays=None):
         cg = self._cg
