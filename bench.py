@@ -279,6 +279,8 @@ def run_ours(args):
         "psdf_enc_double_backward": 12 + 12 + L * 8 + L * 4 * 8 + L * 4 * 8 + C * 4,
         "psdf_sdf_fused_forward": 12 + L * 4 * 8 + 4 + 12 + 128,
         "psdf_sdf_fused_backward": 12 + 2 * L * 4 * 8 + 4 + 12 + 128,
+        "psdf_sdf_fused_forward_multi": 12 + L * 4 * 8 + 4 + 12 + 128,
+        "psdf_sdf_fused_backward_multi": 12 + 2 * L * 4 * 8 + 4 + 12 + 128,
         "psdf_rgb_fused_forward": 12 + L * 4 * 8 + 12 + 12 + 128 + 12,
         "psdf_rgb_fused_backward": 12 + 2 * L * 4 * 8 + 12 + 12 + 128 + 12 + 12 + 128,
     }
@@ -453,6 +455,7 @@ def run_sphere_trace(args):
 
 
 NCU_KERNEL_OF = {"psdf_sdf_fused_forward": "k_sdf_fused<1>", "psdf_sdf_fused_backward": "k_sdf_fused_backward",
+                 "psdf_sdf_fused_forward_multi": "k_sdf_fused<1>", "psdf_sdf_fused_backward_multi": "k_sdf_fused_backward",
                  "psdf_rgb_fused_forward": "k_rgb_fused", "psdf_rgb_fused_backward": "k_rgb_fused_backward",
                  "psdf_sdf_sphere_trace": "k_sdf_sphere_trace"}
 

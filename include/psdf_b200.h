@@ -286,6 +286,76 @@ int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* 
                             float* g_geom, uint8_t* workspace, float* gW0, float* gW1, float* gW2, float* gW3, float* gb0, float* gb1,
                             float* gb2, float* gb3, void* stream);
 
+/* ---------------------------------------------------------------- direct (autograd-free) training iteration
+ * The reference's iteration (permuto_sdf_py/train_permuto_sdf.py:311-422) spends ~70 one-block PyTorch launches between its big kernels
+ * (schedule ramps, Lipschitz normalisation, calibration, loss reductions, zero-fills, gradient adds). These entry points fold them into
+ * the neighbouring kernels; permuto_sdf_b200/train.py Trainer._iteration_direct strings them together. */
+/* two independent sample sets in one psdf_sdf_fused_forward launch (N1 = 0: unused); grad / geom may be NULL per set */
+int psdf_sdf_fused_forward_multi(int L, int T, const float* lattice, const float* scale_factor, const float* shift, const float* window,
+                                 float points_scaling, int hidden, int out_dim, const uint8_t* blob, int N0, const float* pos0, float* sdf0,
+                                 float* grad0, float* geom0, int N1, const float* pos1, float* sdf1, float* grad1, float* geom1, void* stream);
+/* psdf_sdf_mlp_pack + the end-of-iteration counters in the same launch: step_dev [1] (device int, AdamW step count) += 1 and
+ * it_dev [1] (device float, iteration number) += 1; either may be NULL */
+int psdf_sdf_mlp_pack_advance(int in_dim, int hidden, int out_dim, const float* W0, const float* b0, const float* W1, const float* b1,
+                              const float* W2, const float* b2, const float* W3, const float* b3, uint8_t* blob, int* step_dev, float* it_dev,
+                              void* stream);
+/* psdf_rgb_fused_backward with g_sdf_grad accumulated (+=) instead of written */
+int psdf_rgb_fused_backward_acc(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
+                                const float* lattice, const float* scale_factor, const float* shift, const float* window, float points_scaling,
+                                int h1, int h2, int h3, const uint8_t* blob, const float* g_out, float* grad_lattice, float* g_sdf_grad,
+                                float* g_geom, uint8_t* workspace, float* gW0, float* gW1, float* gW2, float* gW3, float* gb0, float* gb1,
+                                float* gb2, float* gb3, void* stream);
+/* psdf_neus_render_loss_forward / _backward with the colour head (Colorcal.calib_RGB_samples_packed + sigmoid, models.py:395-414,677-741)
+ * and the curvature term (models.py:283-294) folded in: x_raw [N,3] is the colour network's linear output; the backward returns
+ * g_sdf [n_rows], g_grad [n_rows,3] (compositing + eikonal + curvature), g_x [n_rows,3], g_grad_shifted [n_rows,3] (curvature term wrt
+ * the gradients at the shifted points; grad_shifted NULL: no curvature term), accumulates the calibration gradients (+=, may be NULL)
+ * and zero-fills rows [nr_valid_dev[0], n_rows) (nr_valid_dev NULL: no tail). curv_scale weighs the curvature MEAN over
+ * nr_samples_dev[0] (or max_nr_samples) rows; scale_eik is divided by the same count. */
+int psdf_neus_head_loss_forward(PSDF_RSP, const float* sdf, const float* grad, const float* x_raw, const float* dirs, const float* dt,
+                                const float* inv_s_dev, float cos_anneal_ratio, const float* cos_anneal_dev, const float* gt_rgb,
+                                const float* gt_mask, const uint8_t* hit, const int* img_idx, const float* weight_delta, const float* bias,
+                                int fixed_img, float* alpha, float* transmittance, float* weights, float* pred_rgb, float* weights_sum,
+                                float* bg_transmittance, float* ray_loss, void* stream);
+int psdf_neus_head_loss_backward(PSDF_RSP, const float* sdf, const float* grad, const float* x_raw, const float* dirs, const float* dt,
+                                 const float* inv_s_dev, float cos_anneal_ratio, const float* cos_anneal_dev, const float* gt_rgb,
+                                 const float* gt_mask, const uint8_t* hit, const int* img_idx, const float* weight_delta, const float* bias,
+                                 int fixed_img, const float* alpha, const float* transmittance, const float* pred_rgb, const float* weights_sum,
+                                 const float* bg_transmittance, float scale_rgb, float scale_mask, float scale_eik, const int* nr_samples_dev,
+                                 const float* grad_shifted, float curv_scale, const float* curv_scale_dev, int n_rows, const int* nr_valid_dev,
+                                 float* g_sdf, float* g_grad, float* g_x, float* g_grad_shifted, float* g_weight_delta, float* g_bias,
+                                 void* stream);
+/* schedule ramps from the device-resident iteration (map_range_val, permuto_sdf_py/utils/common_utils.py:156-160): out[i] = out0 +
+ * (out1 - out0) / (in1 - in0) * (clamp(it, in0, in1) - in0); kinds[i] = 1 / 2: exp(10 * ramp) unclipped / clipped to [1e-6, 1e6]
+ * (inv_s of SingleVarianceNetwork with a forced variance). params [n,4] = {in0, in1, out0, out1} and kinds [n] are HOST arrays, n <= 8;
+ * it_dev [1] device float or NULL (then it_host). */
+int psdf_iter_scalars(int n, const float* params, const int* kinds, const float* it_dev, float it_host, float* out, void* stream);
+/* psdf_lipschitz_normalize of the four colour-MLP matrices + psdf_rgb_mlp_pack of the result in one launch */
+int psdf_lipschitz_pack4(int in_dim, int h1, int h2, int h3, int out_dim, const float* W0, const float* b0, const float* c0, const float* W1,
+                         const float* b1, const float* c1, const float* W2, const float* b2, const float* c2, const float* W3, const float* b3,
+                         const float* c3, uint8_t* blob, void* stream);
+/* psdf_lipschitz_normalize_backward of the four layers in one launch: G_l = d loss / d W_eff_l is consumed and reset to zero,
+ * grad_W_l (+=), grad_c_l (+=); lip_weight != 0 adds d (lip_weight * prod_l softplus(c_l)) / d c_l (LipshitzMLP.lipshitz_bound_full) */
+int psdf_lipschitz_backward4(int in_dim, int h1, int h2, int h3, int out_dim, const float* W0, const float* c0, float* G0, float* gW0, float* gc0,
+                             const float* W1, const float* c1, float* G1, float* gW1, float* gc1, const float* W2, const float* c2, float* G2,
+                             float* gW2, float* gc2, const float* W3, const float* c3, float* G3, float* gW3, float* gc3, float lip_weight,
+                             void* stream);
+/* every scalar loss term of the iteration + the weighted total + the off-surface gradient seed in one launch (see csrc/iter_glue.cu);
+ * acc [8] scratch: zero before the first call, left zero by every call; terms [12] = {sum L1, sum BCE, sum eikonal, mean curvature,
+ * mean off-surface, Lipschitz bound, valid rows, divisor of the per-sample means, loss_rgb, loss_eikonal, unused, unused} */
+int psdf_loss_terms(int N, const int* nr_valid_dev, const int* nr_mean_dev, const float* grad, const float* grad_shifted, int R,
+                    const float* ray_loss, int n_off, const float* sdf_off, float* g_off, float c_rgb, float c_mask, float w_eik, float w_curv,
+                    const float* w_curv_dev, float w_off, float w_lip, const float* lip_c0, const float* lip_c1, const float* lip_c2,
+                    const float* lip_c3, float* acc, float* loss, float* terms, void* stream);
+/* Sphere.rand_points_inside (src/Sphere.cu) from ONE uniform draw u01 [3,n]: rows = phi / (2 pi), (cos(theta) + 1) / 2, u */
+int psdf_sphere_rand_points_inside_u01(int n, float radius, const float* u01, float* out, void* stream);
+/* psdf_adamw_step over up to 8 parameter groups in one launch: device-resident step count, per-group hyper_dev [2] = {lr, weight_decay};
+ * gradients scaled by grad_scale and reset to zero. n_l % 4 == 0, 16-byte aligned pointers. n and the five tables of device addresses
+ * (one entry per group) are HOST arrays. The step used is step_dev[0] + step_offset (step_offset = 1: the counter is advanced afterwards
+ * by psdf_sdf_mlp_pack_advance). */
+int psdf_adamw_multi_step(int n_groups, const long long* n, const uint64_t* param, const uint64_t* grad, const uint64_t* exp_avg,
+                          const uint64_t* exp_avg_sq, const uint64_t* hyper_dev, float beta1, float beta2, float eps, const int* step_dev,
+                          int step_offset, float grad_scale, void* stream);
+
 /* ---------------------------------------------------------------- dense fused AdamW (torch.optim.AdamW / apex FusedAdam math,
  * train_permuto_sdf.py:293-304); step >= 1 is the incremented step count; grad is multiplied by grad_scale and, when
  * zero_grad != 0, reset to zero in the same pass. Pointers 16-byte aligned. step_dev [1] (device int32), when not NULL,

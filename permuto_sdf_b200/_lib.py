@@ -143,7 +143,10 @@ def call(name, *args):
             conv.append(int(a))
     if _STATS is not None:
         _STATS["calls"][name] = _STATS["calls"].get(name, 0) + 1
-        if args and isinstance(args[0], int):            # leading count argument (samples / rays) of the entry point
+        if name in _UNITS_FN:                            # samples processed by a multi-set launch
+            u = _STATS.setdefault("units", {})
+            u[name] = u.get(name, 0) + _UNITS_FN[name](args)
+        elif args and isinstance(args[0], int):          # leading count argument (samples / rays) of the entry point
             u = _STATS.setdefault("units", {})
             u[name] = u.get(name, 0) + int(args[0])
         if name in _KERNELS_FN:
@@ -177,7 +180,9 @@ def _bwd_kernels(args):
     return 2 * max(1, (tiles + chunk - 1) // chunk)
 
 
-_KERNELS_FN = {"psdf_rgb_fused_backward": _bwd_kernels}
+_KERNELS_FN = {"psdf_rgb_fused_backward": _bwd_kernels, "psdf_rgb_fused_backward_acc": _bwd_kernels}
+_UNITS_FN = {"psdf_sdf_fused_forward_multi": lambda a: int(a[10]) + int(a[15]),
+             "psdf_sdf_fused_backward_multi": lambda a: int(a[10]) + int(a[15]) + int(a[20])}
 _STATS = None
 LAST_UNITS = {}        # {entry point: sum of its leading count argument} of the last stats window
 

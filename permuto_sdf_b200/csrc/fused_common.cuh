@@ -53,7 +53,14 @@ inline MlpGeom make_geom(int in_dim, int hidden, int out_dim) {
 // second half of the blob: the same weights transposed (rows = input features, K = output features) for the
 // backward GEMMs dA = dZ * W
 static __global__ void k_pack_mlp(MlpGeom g, const float* W0, const float* b0, const float* W1, const float* b1, const float* W2,
-                                  const float* b2, const float* W3, const float* b3, uint8_t* blob) {
+                                  const float* b2, const float* W3, const float* b3, uint8_t* blob, int* step_inc = nullptr,
+                                  float* it_inc = nullptr) {
+    // end-of-iteration bookkeeping folded into the re-pack that closes an optimizer step: AdamW step count and iteration number, both
+    // device resident under CUDA-graph replay (every kernel that read them in this iteration has completed: same stream)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+        if (step_inc) step_inc[0] += 1;
+        if (it_inc) it_inc[0] += 1.0f;
+    }
     const float* W[kNL] = {W0, W1, W2, W3};
     const float* B[kNL] = {b0, b1, b2, b3};
     int l = blockIdx.y;

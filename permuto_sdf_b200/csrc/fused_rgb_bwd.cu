@@ -244,7 +244,9 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
                         const float d = nx * bx + ny * by + nz * bz;
                         ox -= nx * d * inv; oy -= ny * d * inv; oz -= nz * d * inv;
                     }
-                    g_sdf_grad[(size_t)n * 3] = ox; g_sdf_grad[(size_t)n * 3 + 1] = oy; g_sdf_grad[(size_t)n * 3 + 2] = oz;
+                    float* o = g_sdf_grad + (size_t)n * 3;
+                    if (P.acc_sdf_grad) { o[0] += ox; o[1] += oy; o[2] += oz; }
+                    else { o[0] = ox; o[1] = oy; o[2] = oz; }
                 }
             }
         }
@@ -377,14 +379,15 @@ long long psdf_rgb_fused_backward_workspace_bytes(int N) {
     return (long long)2 * kNL * rgb_bwd_chunk_tiles(ntiles) * kRgbSpillBytes;
 }
 
-int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
+static int rgb_backward_impl(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
                             const float* lattice, const float* scale_factor, const float* shift, const float* window, float points_scaling,
                             int h1, int h2, int h3, const uint8_t* blob, const float* g_out, float* grad_lattice, float* g_sdf_grad,
                             float* g_geom, uint8_t* workspace, float* gW0, float* gW1, float* gW2, float* gW3, float* gb0, float* gb1,
-                            float* gb2, float* gb3, void* stream) {
+                            float* gb2, float* gb3, int accumulate_sdf_grad, void* stream) {
     RgbParams P;
     int rc = make_rgb_params(P, N, L, T, geom_dim, points_scaling, h1, h2, h3);
     if (rc != PSDF_OK) return rc;
+    P.acc_sdf_grad = accumulate_sdf_grad ? 1 : 0;
     if (N == 0) return PSDF_OK;
     if ((size_t)128 * (P.g.Kp[0] + 1) * 4 > (size_t)2 * kWTileBytes) return PSDF_ERR_UNSUPPORTED;
     RgbSpill sp;
@@ -418,6 +421,24 @@ int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* 
         PSDF_CHECK_LAUNCH();
     }
     return PSDF_OK;
+}
+
+int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
+                            const float* lattice, const float* scale_factor, const float* shift, const float* window, float points_scaling,
+                            int h1, int h2, int h3, const uint8_t* blob, const float* g_out, float* grad_lattice, float* g_sdf_grad,
+                            float* g_geom, uint8_t* workspace, float* gW0, float* gW1, float* gW2, float* gW3, float* gb0, float* gb1,
+                            float* gb2, float* gb3, void* stream) {
+    return rgb_backward_impl(N, L, T, pos, dirs, sdf_grad, geom, geom_dim, lattice, scale_factor, shift, window, points_scaling, h1, h2, h3, blob,
+                             g_out, grad_lattice, g_sdf_grad, g_geom, workspace, gW0, gW1, gW2, gW3, gb0, gb1, gb2, gb3, 0, stream);
+}
+// same, with g_sdf_grad accumulated (+=): the buffer already holds d loss / d sdf_grad of the compositing and curvature terms
+int psdf_rgb_fused_backward_acc(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
+                                const float* lattice, const float* scale_factor, const float* shift, const float* window, float points_scaling,
+                                int h1, int h2, int h3, const uint8_t* blob, const float* g_out, float* grad_lattice, float* g_sdf_grad,
+                                float* g_geom, uint8_t* workspace, float* gW0, float* gW1, float* gW2, float* gW3, float* gb0, float* gb1,
+                                float* gb2, float* gb3, void* stream) {
+    return rgb_backward_impl(N, L, T, pos, dirs, sdf_grad, geom, geom_dim, lattice, scale_factor, shift, window, points_scaling, h1, h2, h3, blob,
+                             g_out, grad_lattice, g_sdf_grad, g_geom, workspace, gW0, gW1, gW2, gW3, gb0, gb1, gb2, gb3, 1, stream);
 }
 
 }  // extern "C"

@@ -27,6 +27,7 @@ struct RgbParams {
     float points_scaling;
     int enc_cols;        // 2L + 4
     int in_dim;          // enc_cols + 25 + 3 + 32
+    int acc_sdf_grad = 0; // backward: g_sdf_grad += instead of = (the caller's buffer already holds the compositing / curvature terms)
     MlpGeom g;
 };
 

@@ -33,13 +33,22 @@ namespace {
 // SM, each on its own tile with its own barriers, so that one CTA's MMA / barrier / gather waits are filled by the other's work.
 constexpr int kFusedThreads = 512;
 constexpr int kValueThreads = 256;
+// Up to two independent sample sets per launch (the main samples and the off-surface points of a training iteration): each set starts on
+// a tile boundary and has its own outputs (grad / geom may be NULL per set).
+struct FwdSegs {
+    int n[2];
+    int tile0[3];
+    const float* pos[2];
+    float* sdf[2];
+    float* grad[2];
+    float* geom[2];
+};
 template <bool TAN> struct FwdCfg { static constexpr int kThreads = TAN ? kFusedThreads : kValueThreads; static constexpr int kCtasPerSm = TAN ? 1 : 2; };
 
 template <bool TAN>
 __global__ void __launch_bounds__(FwdCfg<TAN>::kThreads, FwdCfg<TAN>::kCtasPerSm)
-k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restrict__ lattice, const float* __restrict__ scale,
-            const float* __restrict__ shift, const float* __restrict__ window, const uint8_t* __restrict__ blob,
-            float* __restrict__ sdf_out, float* __restrict__ grad_out, float* __restrict__ geom_out) {
+k_sdf_fused(FusedParams P, FwdSegs G, const float2* __restrict__ lattice, const float* __restrict__ scale,
+            const float* __restrict__ shift, const float* __restrict__ window, const uint8_t* __restrict__ blob) {
     constexpr int S = TAN ? 4 : 1;
     constexpr int kThreads = FwdCfg<TAN>::kThreads, kGroups = kThreads / kTile;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -76,10 +85,15 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
     const int level_cores = P.L / 4;                        // 4 levels x 2 features = one 16-byte core row
     const int all_cores = P.g.Kp[0] / 8;
 
-    const int ntiles = (P.N + kTile - 1) / kTile;
+    const int ntiles = G.tile0[2];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int n = tile * kTile + row;
-        const bool valid = n < P.N;
+        const int seg = tile >= G.tile0[1] ? 1 : 0;                   // every sample set starts on a tile boundary
+        const int n = (tile - G.tile0[seg]) * kTile + row;           // row inside its set
+        const bool valid = n < G.n[seg];
+        const float* __restrict__ pos = G.pos[seg];
+        float* __restrict__ sdf_out = G.sdf[seg];
+        float* __restrict__ grad_out = G.grad[seg];
+        float* __restrict__ geom_out = G.geom[seg];
         float x[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) x[i] = valid ? pos[(size_t)n * 3 + i] : 0.0f;
@@ -209,7 +223,7 @@ k_sdf_fused(FusedParams P, const float* __restrict__ pos, const float2* __restri
                     const int nout = P.g.N[l];
                     if (c == 0) {
                         sdf_out[n] = z[0];
-                        if (TAN) { grad_out[(size_t)n * 3] = tz[0][0]; grad_out[(size_t)n * 3 + 1] = tz[1][0]; grad_out[(size_t)n * 3 + 2] = tz[2][0]; }
+                        if (TAN && grad_out) { grad_out[(size_t)n * 3] = tz[0][0]; grad_out[(size_t)n * 3 + 1] = tz[1][0]; grad_out[(size_t)n * 3 + 2] = tz[2][0]; }
                     }
                     if (geom_out) {
 #pragma unroll
@@ -664,13 +678,25 @@ int psdf_sdf_mlp_pack(int in_dim, int hidden, int out_dim, const float* W0, cons
     return PSDF_OK;
 }
 
-int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
-                           const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, float* sdf,
-                           float* grad, float* geom, void* stream) {
-    if (N < 0 || L < 1 || L > kMaxLevels || (L % 4) != 0 || hidden > 64 || hidden % 16 != 0 || out_dim > 64) return PSDF_ERR_UNSUPPORTED;
-    if (N == 0) return PSDF_OK;
+// psdf_sdf_mlp_pack + the end-of-iteration counters in the same launch: step_dev [1] (int, AdamW step count) += 1 and it_dev [1] (float,
+// iteration number) += 1 (either may be NULL)
+int psdf_sdf_mlp_pack_advance(int in_dim, int hidden, int out_dim, const float* W0, const float* b0, const float* W1, const float* b1,
+                              const float* W2, const float* b2, const float* W3, const float* b3, uint8_t* blob, int* step_dev, float* it_dev,
+                              void* stream) {
+    if (hidden > 64 || out_dim > 64 || in_dim > 64) return PSDF_ERR_UNSUPPORTED;
+    MlpGeom g = make_geom(in_dim, hidden, out_dim);
+    dim3 grid(div_up(64 * 64, 256), kNL);
+    k_pack_mlp<<<grid, 256, 0, ST>>>(g, W0, b0, W1, b1, W2, b2, W3, b3, blob, step_dev, it_dev);
+    PSDF_CHECK_LAUNCH();
+    return PSDF_OK;
+}
+
+static int launch_forward(int L, int T, const float* lattice, const float* scale_factor, const float* shift, const float* window,
+                          float points_scaling, int hidden, int out_dim, const uint8_t* blob, int nseg, const int* Ns, const float* const* pos,
+                          float* const* sdf, float* const* grad, float* const* geom, void* stream) {
+    if (L < 1 || L > kMaxLevels || (L % 4) != 0 || hidden > 64 || hidden % 16 != 0 || out_dim > 64) return PSDF_ERR_UNSUPPORTED;
     FusedParams P;
-    P.N = N; P.L = L; P.T = T;
+    P.L = L; P.T = T;
     P.cap_mask = t_magic(T);
     P.points_scaling = points_scaling;
     P.in_dim = (L + 2) * 2;                       // D = 3, F = 2: E = 2 concat levels
@@ -678,22 +704,57 @@ int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* l
     static const int free_levels = getenv("PSDF_EXPERIMENT_FREE_LEVELS") ? atoi(getenv("PSDF_EXPERIMENT_FREE_LEVELS")) : 0;
     P.free_levels = free_levels;
     P.g = make_geom(P.in_dim, hidden, out_dim);
+    FwdSegs G;
+    int tiles = 0, total = 0;
+    bool tangents = false;
+    for (int i = 0; i < 2; i++) {
+        const int n = i < nseg ? Ns[i] : 0;
+        if (n < 0) return PSDF_ERR_ARG;
+        G.n[i] = n; G.tile0[i] = tiles;
+        G.pos[i] = n ? pos[i] : nullptr; G.sdf[i] = n ? sdf[i] : nullptr; G.grad[i] = n ? grad[i] : nullptr; G.geom[i] = n ? geom[i] : nullptr;
+        if (n && (!pos[i] || !sdf[i])) return PSDF_ERR_ARG;
+        tangents = tangents || (n && grad[i]);
+        tiles += div_up(n, kTile);
+        total += n;
+    }
+    G.tile0[2] = tiles;
+    P.N = total;
+    if (tiles == 0) return PSDF_OK;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int ntiles = div_up(N, kTile);
     const float2* lat = reinterpret_cast<const float2*>(lattice);
-    if (grad) {
+    if (tangents) {
         size_t smem = (size_t)P.g.total + 4 * 2 * kATileBytes + sizeof(LevelC) + 64;
         { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_fused<true>, 227 * 1024, optin_); }
-        k_sdf_fused<true><<<min(ntiles, sms), kFusedThreads, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
+        k_sdf_fused<true><<<min(tiles, sms), kFusedThreads, smem, ST>>>(P, G, lat, scale_factor, shift, window, blob);
     } else {
         size_t smem = (size_t)P.g.total + 2 * kATileBytes + sizeof(LevelC) + 64;
         { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_fused<false>, 113 * 1024, optin_); }
-        k_sdf_fused<false><<<min(ntiles, 2 * sms), kValueThreads, smem, ST>>>(P, pos, lat, scale_factor, shift, window, blob, sdf, grad, geom);
+        k_sdf_fused<false><<<min(tiles, 2 * sms), kValueThreads, smem, ST>>>(P, G, lat, scale_factor, shift, window, blob);
     }
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
+}
+
+int psdf_sdf_fused_forward(int N, int L, int T, const float* pos, const float* lattice, const float* scale_factor, const float* shift,
+                           const float* window, float points_scaling, int hidden, int out_dim, const uint8_t* blob, float* sdf,
+                           float* grad, float* geom, void* stream) {
+    if (N < 0) return PSDF_ERR_UNSUPPORTED;
+    return launch_forward(L, T, lattice, scale_factor, shift, window, points_scaling, hidden, out_dim, blob, 1, &N, &pos, &sdf, &grad, &geom, stream);
+}
+
+// Two independent sample sets in ONE launch (the main samples of a training iteration and its off-surface points: 8 tiles more instead
+// of a second, latency-bound launch of 8 CTAs). Value + tangent kernel when either set asks for its gradient.
+int psdf_sdf_fused_forward_multi(int L, int T, const float* lattice, const float* scale_factor, const float* shift, const float* window,
+                                 float points_scaling, int hidden, int out_dim, const uint8_t* blob, int N0, const float* pos0, float* sdf0,
+                                 float* grad0, float* geom0, int N1, const float* pos1, float* sdf1, float* grad1, float* geom1, void* stream) {
+    const int Ns[2] = {N0, N1};
+    const float* pos[2] = {pos0, pos1};
+    float* sdf[2] = {sdf0, sdf1};
+    float* grad[2] = {grad0, grad1};
+    float* geom[2] = {geom0, geom1};
+    return launch_forward(L, T, lattice, scale_factor, shift, window, points_scaling, hidden, out_dim, blob, 2, Ns, pos, sdf, grad, geom, stream);
 }
 
 int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream) {

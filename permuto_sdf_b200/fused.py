@@ -69,11 +69,16 @@ class FusedSDF:
     def _cur_versions(self):
         return tuple(p._version for l in self.lin for p in (l.weight, l.bias))
 
-    def repack(self):
-        """weights -> tensor-core operand blob (call after every optimizer step; cheap, one small kernel)"""
+    def repack(self, advance=None):
+        """weights -> tensor-core operand blob (call after every optimizer step; cheap, one small kernel). advance = (step_dev, it_dev):
+        the same launch also increments the device-resident AdamW step count and iteration number (either may be None)"""
         l = self.lin
-        call("psdf_sdf_mlp_pack", self.in_dim, self.hidden, self.out_dim, l[0].weight.detach(), l[0].bias.detach(), l[1].weight.detach(),
-             l[1].bias.detach(), l[2].weight.detach(), l[2].bias.detach(), l[3].weight.detach(), l[3].bias.detach(), self.blob)
+        w = (l[0].weight.detach(), l[0].bias.detach(), l[1].weight.detach(), l[1].bias.detach(), l[2].weight.detach(), l[2].bias.detach(),
+             l[3].weight.detach(), l[3].bias.detach())
+        if advance is not None:
+            call("psdf_sdf_mlp_pack_advance", self.in_dim, self.hidden, self.out_dim, *w, self.blob, advance[0], advance[1])
+        else:
+            call("psdf_sdf_mlp_pack", self.in_dim, self.hidden, self.out_dim, *w, self.blob)
         self._versions = self._cur_versions()
 
     # ------------------------------------------------------------------------------------------ training path
@@ -493,10 +498,10 @@ class CurvatureLossFn(torch.autograd.Function):
         return gg, ggs, None
 
 
-def curvature_shifted_points(points, sdf_gradients, epsilon=1e-4):
+def curvature_shifted_points(points, sdf_gradients, epsilon=1e-4, rnd=None):
     """points + eps * cross(normalize(sdf_gradients), normalize(randn)) (models.py:266-273), no autograd (the shifted points only feed
     a forward whose position gradient is not propagated)"""
-    rnd = torch.randn_like(points)
+    rnd = torch.randn_like(points) if rnd is None else rnd.contiguous()
     out = torch.empty_like(points)
     call("psdf_curvature_shift_points", points.shape[0], points.detach().contiguous(), sdf_gradients.detach().contiguous(), rnd, float(epsilon), out)
     return out

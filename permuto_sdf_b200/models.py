@@ -279,11 +279,11 @@ class SDF(torch.nn.Module, _Checkpointed):
         return sdf_shifted, angle / math.pi
 
 
-    def curvature_loss(self, points, sdf_gradients, iter_nr, nr_valid_dev=None):
+    def curvature_loss(self, points, sdf_gradients, iter_nr, nr_valid_dev=None, rnd=None):
         """mean curvature of get_sdf_and_curvature_1d_precomputed_gradient_normal_based over the valid samples with the element-wise
         chain in three kernels (csrc/rgb_misc.cu); the SDF evaluation at the shifted points is the usual (fused) one"""
         from .fused import CurvatureLossFn, curvature_shifted_points
-        shifted = curvature_shifted_points(points, sdf_gradients)
+        shifted = curvature_shifted_points(points, sdf_gradients, rnd=rnd)
         _, grads_shifted, _ = self.get_sdf_and_gradient(shifted, iter_nr)
         return CurvatureLossFn.apply(sdf_gradients, grads_shifted, nr_valid_dev)
 

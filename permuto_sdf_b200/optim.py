@@ -156,15 +156,43 @@ class FusedAdamW:
             self.hyper_dev.copy_(self._hyper_host, non_blocking=True)
             self._hyper_cached = cur
 
+    def _multi_tables(self):
+        """host tables of device addresses for psdf_adamw_multi_step (all groups in one launch)"""
+        import ctypes
+        gs = [g for g in self.param_groups if g["_n"] > 0]
+        k = len(gs)
+        n = (ctypes.c_longlong * k)(*[g["_n"] for g in gs])
+        tab = lambda base: (ctypes.c_uint64 * k)(*[base.data_ptr() + 4 * g["_off"] for g in gs])
+        idx = [self.param_groups.index(g) for g in gs]
+        hyper = (ctypes.c_uint64 * k)(*[self.hyper_dev.data_ptr() + 8 * i for i in idx])
+        key = (self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.hyper_dev.data_ptr())
+        return dict(key=key, k=k, n=n, p=tab(self.flat_param), g=tab(self.flat_grad), m=tab(self.exp_avg), v=tab(self.exp_avg_sq), h=hyper)
+
     @torch.no_grad()
-    def step(self, grad_scale=1.0, groups=None, advance=True):
+    def step(self, grad_scale=1.0, groups=None, advance=True, defer_counter=False):
         """groups: indices of the param groups to sweep (None: all). advance=False: a second call of the same optimizer step (the
-        data-parallel path steps the colour hash table while the other gradients are still being all-reduced)."""
+        data-parallel path steps the colour hash table while the other gradients are still being all-reduced).
+        defer_counter=True (device-resident step count, all groups): ONE launch sweeps every group with step = step_dev + 1 and the
+        counter itself is advanced by the caller's psdf_sdf_mlp_pack_advance (Trainer: the re-pack that closes the iteration)."""
         if self._peer is not None:
             return self._peer_step(grad_scale, advance)
         if advance:
             self.step_count += 1
         b1, b2 = self.betas
+        if defer_counter and self.device_step and groups is None and advance and len(self.param_groups) <= 8:
+            import ctypes
+            if self.step_dev is None:
+                self.step_dev = torch.full((1,), self.step_count - 1, dtype=torch.int32, device=self.flat_param.device)
+            if self.hyper_dev is None:
+                self.sync_hyper()
+            mt = getattr(self, "_multi", None)
+            if mt is None or mt["key"] != (self.flat_param.data_ptr(), self.flat_grad.data_ptr(), self.hyper_dev.data_ptr()):
+                mt = self._multi = self._multi_tables()
+            call("psdf_adamw_multi_step", mt["k"], ctypes.addressof(mt["n"]), ctypes.addressof(mt["p"]), ctypes.addressof(mt["g"]),
+                 ctypes.addressof(mt["m"]), ctypes.addressof(mt["v"]), ctypes.addressof(mt["h"]), b1, b2, self.eps, self.step_dev, 1,
+                 float(grad_scale))
+            self._clean = True
+            return True
         step_dev = None
         if self.device_step:            # CUDA-graph mode: the step counter lives (and is incremented) on the device
             if self.step_dev is None:

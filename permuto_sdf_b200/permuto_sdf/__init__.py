@@ -249,6 +249,15 @@ class Sphere:
         call("psdf_sphere_rand_points_inside", n, self.m_radius, phi, costheta, u, pts)
         return pts
 
+    def rand_points_inside_u01(self, u01):
+        """rand_points_inside from ONE uniform draw u01 [3,n] in [0,1) (rows: phi / 2 pi, (cos theta + 1) / 2, u): one RNG launch and one
+        kernel instead of three and one (not in the reference; used by the training iteration for its off-surface points)"""
+        u = _f32(u01, "u01").contiguous()
+        n = u.shape[1]
+        pts = torch.empty(n, 3, device=u.device)
+        call("psdf_sphere_rand_points_inside_u01", n, self.m_radius, u, pts)
+        return pts
+
     def check_point_inside_primitive(self, points):
         p = _f32(points, "points", 3)
         out = torch.empty(p.shape[0], 1, dtype=torch.bool, device=p.device)

@@ -319,7 +319,9 @@ class Trainer:
     per-iteration step of train_permuto_sdf.py:311-422 (after sphere init), with `--with_mask` semantics."""
 
     def __init__(self, hyperparams=None, nr_levels=24, capacity=2 ** 18, sdf_hidden=32, nr_images=8, occupancy_resolution=256,
-                 seed=0, with_colorcal=True, optimizer="adamw", fused_inference=True, fused_training=True, fused_render=True):
+                 seed=0, with_colorcal=True, optimizer="adamw", fused_inference=True, fused_training=True, fused_render=True, direct=None):
+        """direct: None = run the iteration through the autograd-free sequence of iteration.DirectIteration whenever the configuration
+        allows it (fused kernels, flat-buffer optimizer, --with_mask); True = require it (raise otherwise); False = autograd formulation"""
         torch.manual_seed(seed)
         self.fused_render = fused_render
         self._fused_inference = fused_inference
@@ -360,6 +362,16 @@ class Trainer:
                     m.encoding.grad_in_place = True
         else:
             self.optimizer = torch.optim.AdamW(groups, amsgrad=False, betas=(0.9, 0.99), eps=1e-15, weight_decay=0.0, lr=hp.lr)
+        # the iteration itself: explicit kernel sequence (iteration.py) or torch.autograd around the same kernels
+        from .iteration import DirectIteration
+        self.fixed_random = None        # tests: {"offsurface_u01": [3,1024], "curvature_dirs": [N,3]} replace the torch RNG draws
+        self._direct = None
+        why = DirectIteration.unsupported_reason(self) if direct is not False else "disabled by the caller (direct=False)"
+        if why is None:
+            self._direct = DirectIteration(self)
+        elif direct:
+            raise RuntimeError("Trainer(direct=True): " + why)
+        self.execution["iteration"] = "direct kernel sequence (iteration.py)" if self._direct is not None else "torch.autograd (%s)" % why
         self.iter_nr = 0
         self._cg = None                 # CUDA-graph state (enable_cuda_graph)
         self._dp = None                 # data-parallel state (enable_data_parallel)
@@ -408,6 +420,22 @@ class Trainer:
         sdf = (pts.norm(dim=1, keepdim=True) - object_radius).contiguous()
         g.update_with_sdf(sdf, inv_s, 1e10, 1e-4)
 
+    def draw(self, name, fn):
+        """random draw `name` of the iteration: fn() (torch RNG) unless a test pinned it in self.fixed_random"""
+        fr = self.fixed_random
+        return fr[name] if (fr is not None and name in fr) else fn()
+
+    def forward_backward(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal):
+        """losses + backward of one iteration; parameter gradients are ACCUMULATED into .grad (the caller has run
+        optimizer.zero_grad(); outside any graph capture). -> detached loss"""
+        if self._direct is not None:
+            loss = self._direct.run(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal)
+            if loss is not None:
+                return loss
+        loss = self.losses(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal)
+        loss.backward()
+        return loss.detach()
+
     def losses(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal):
         hp = self.hp
         cos_anneal_ratio = map_range_val(iter_nr_for_anneal, 0.0, hp.forced_variance_finish_iter, 0.0, 1.0)
@@ -435,8 +463,9 @@ class Trainer:
         loss_curv = torch.zeros((), device=loss.device)
         if iter_nr_for_anneal < hp.iter_finish_reduce_curv and fg.samples_pos.shape[0] != 0:      # <=> gw_curv > 0
             if self.fused_render:
+                rnd = self.draw("curvature_dirs", lambda: torch.randn_like(fg.samples_pos))
                 loss_curv = self.model_sdf.curvature_loss(fg.samples_pos, sdf_gradients, iter_nr_for_anneal,
-                                                          fg.cur_nr_samples if RaySamplesPacked.static_capacity else None)
+                                                          fg.cur_nr_samples if RaySamplesPacked.static_capacity else None, rnd=rnd)
                 if getattr(fg, "dp_mean_nr_samples", None) is not None:       # mean over the samples of all ranks (see run_net)
                     loss_curv = loss_curv * (fg.cur_nr_samples.float() / fg.dp_mean_nr_samples.float()).squeeze(0)
             else:
@@ -450,7 +479,8 @@ class Trainer:
                     loss_curv = curv.mean()
             loss = loss + loss_curv * hp.curvature_weight * gw_curv
         if hp.use_occupancy_grid:
-            off = self.aabb.rand_points_inside(nr_points=1024)
+            u01 = self.draw("offsurface_u01", lambda: torch.rand(3, 1024, device=loss.device))
+            off = self.aabb.rand_points_inside_u01(u01)
             sdf_rand, _ = self.model_sdf(off, iter_nr_for_anneal)
             loss = loss + torch.exp(-1e2 * torch.abs(sdf_rand)).mean() * hp.offsurface_weight
         if iter_nr_for_anneal >= hp.iter_start_reduce_curv:      # the bound is only part of the loss from here on
@@ -589,7 +619,9 @@ class Trainer:
         if self._cg is not None:
             return self._step_graphed(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy, optimizer_step)
         it = self.iter_nr
-        loss = self.losses(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, it)
+        self.optimizer.zero_grad(set_to_none=False)
+        loss = self.forward_backward(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, it)
+        self._dp_join_backward()
         if update_occupancy is None:
             update_occupancy = (it % 8 == 0)
         if update_occupancy and self.hp.use_occupancy_grid:
@@ -597,13 +629,10 @@ class Trainer:
         if self.hp.adaptive_nr_rays:
             self.adapt_nr_rays(int(self.last["nr_samples"]))
         self.apply_schedules(it)
-        self.optimizer.zero_grad(set_to_none=False)
-        loss.backward()
-        self._dp_join_backward()
         if optimizer_step:
             self.optimizer_step()
         self.iter_nr += 1
-        return loss.detach()
+        return loss
 
     # ------------------------------------------------------------------------------------ CUDA-graph replay
     def enable_cuda_graph(self, warmup_steps=3):
@@ -678,11 +707,9 @@ class Trainer:
                 if make_rays is not None:
                     with torch.no_grad():
                         args = make_rays(*[t.to(cg["it_dev"].device, non_blocking=True) for t in inputs])
-                loss = self.losses(*args, DeviceIter(it, cg["it_dev"]))
                 self.optimizer.zero_grad(set_to_none=False)
-                loss.backward()
+                loss = self.forward_backward(*args, DeviceIter(it, cg["it_dev"]))
                 self._dp_join_backward()
-                loss = loss.detach()
             cur.wait_stream(side)
         else:
             if not valid:
@@ -753,10 +780,8 @@ class Trainer:
             if make_rays is not None:
                 with torch.no_grad():
                     args = make_rays(*static)
-            loss = self.losses(*args, dit)
-            loss.backward()
+            out = self.forward_backward(*args, dit)
             self._dp_join_backward()
-            out = loss.detach()
         _, launches, _ = stats_end()
         dp_rgb = bool(self._dp.pop("rgb_reduced", False)) if getattr(self, "_dp", None) is not None else False
         cg["occ"] = None               # the refresh graph reads tensors of the iteration graph (last inv_s): capture it again
@@ -775,15 +800,19 @@ class Trainer:
             rgb_done = False
 
         def work():
+            deferred = False
             if dp is not None:
                 self._dp_optimizer_step(rgb_done)
             else:
                 if allreduce:
                     import torch.distributed as dist
                     dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
-                self.optimizer.step(grad_scale=grad_scale)
-            self.model_sdf.fused.repack()
-            cg["it_dev"].add_(1.0)
+                # every group in one launch; the step counter is advanced by the re-pack below (2 launches instead of 7)
+                deferred = self.optimizer.step(grad_scale=grad_scale, defer_counter=True) is True
+            if deferred:
+                self.model_sdf.fused.repack(advance=(self.optimizer.step_dev, cg["it_dev"]))
+            else:
+                self.model_sdf.fused.repack(advance=(None, cg["it_dev"]))
 
         if cg["fb"] is None:            # still in the eager warm-up iterations
             side, cur = cg["stream"], torch.cuda.current_stream()
