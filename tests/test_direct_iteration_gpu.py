@@ -163,7 +163,7 @@ def test_glue_kernels_match_the_per_op_kernels(cuda):
     for l in range(4):
         assert rel(acc_w[l] - 0.5, ref_gw[l]) < 1e-5
         lip_g = lip_w * prod / sp[l] * torch.sigmoid(c[l].double())
-        assert abs(float(acc_c[l]) - 0.25 - float(ref_gc[l]) - float(lip_g)) <= 1e-5 * (abs(float(ref_gc[l])) + 1e-6)
+        assert abs(float(acc_c[l]) - 0.25 - float(ref_gc[l]) - float(lip_g)) <= 1e-5 * (abs(float(ref_gc[l])) + abs(float(lip_g))) + 1e-7
         assert float(Gc[l].abs().max()) == 0.0
     # ---- two sample sets in one forward launch == two launches
     from permuto_sdf_b200.models import SDF
