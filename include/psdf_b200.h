@@ -290,6 +290,9 @@ int psdf_rgb_fused_backward(int N, int L, int T, const float* pos, const float* 
  * The reference's iteration (permuto_sdf_py/train_permuto_sdf.py:311-422) spends ~70 one-block PyTorch launches between its big kernels
  * (schedule ramps, Lipschitz normalisation, calibration, loss reductions, zero-fills, gradient adds). These entry points fold them into
  * the neighbouring kernels; permuto_sdf_b200/train.py Trainer._iteration_direct strings them together. */
+/* kernel variant of the value + tangent forward (A/B measurements): 1 = two independent 64-sample groups per CTA (default),
+ * 0 = lock-step 128-sample tiles; any other value only queries. Returns the variant in use. Same results to the last bit. */
+int psdf_sdf_forward_variant(int variant);
 /* two independent sample sets in one psdf_sdf_fused_forward launch (N1 = 0: unused); grad / geom may be NULL per set */
 int psdf_sdf_fused_forward_multi(int L, int T, const float* lattice, const float* scale_factor, const float* shift, const float* window,
                                  float points_scaling, int hidden, int out_dim, const uint8_t* blob, int N0, const float* pos0, float* sdf0,

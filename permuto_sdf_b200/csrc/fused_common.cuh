@@ -179,6 +179,10 @@ struct FusedParams {
     int in_dim;          // (L + E) * 2 feature columns
     int free_levels = 0; // diagnostics only (PSDF_EXPERIMENT_FREE_LEVELS): the gathers of levels < free_levels read nothing (upper bound of
                          // what staging those levels' table entries in shared memory could save); 0 in production
+    int skew = 1;        // k_sdf_fused_dual: group 1 starts half a sub-tile after group 0 (PSDF_SDF_FWD_SKEW=0 disables, A/B measurements)
+    int knockout = 0;    // diagnostics only (PSDF_EXPERIMENT_KNOCKOUT, k_sdf_fused<true>): bit 0 skip the encoder, bit 1 issue no MMA, bit 2 skip
+                         // the GELU arithmetic, bit 3 skip the operand-tile stores of the epilogue -- "what would this phase cost if it were
+                         // free" timings (results are garbage); 0 in production
     MlpGeom g;
 };
 

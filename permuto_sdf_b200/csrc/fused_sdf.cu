@@ -87,19 +87,19 @@ k_sdf_fused(FusedParams P, FwdSegs G, const float2* __restrict__ lattice, const 
 
     const int ntiles = G.tile0[2];
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int seg = tile >= G.tile0[1] ? 1 : 0;                   // every sample set starts on a tile boundary
-        const int n = (tile - G.tile0[seg]) * kTile + row;           // row inside its set
-        const bool valid = n < G.n[seg];
-        const float* __restrict__ pos = G.pos[seg];
-        float* __restrict__ sdf_out = G.sdf[seg];
-        float* __restrict__ grad_out = G.grad[seg];
-        float* __restrict__ geom_out = G.geom[seg];
+        const bool seg1 = tile >= G.tile0[1];                         // every sample set starts on a tile boundary
+        const int n = (tile - (seg1 ? G.tile0[1] : 0)) * kTile + row;   // row inside its set
+        const bool valid = n < (seg1 ? G.n[1] : G.n[0]);
+        const float* __restrict__ pos = seg1 ? G.pos[1] : G.pos[0];
+        float* __restrict__ sdf_out = seg1 ? G.sdf[1] : G.sdf[0];
+        float* __restrict__ grad_out = seg1 ? G.grad[1] : G.grad[0];
+        float* __restrict__ geom_out = seg1 ? G.geom[1] : G.geom[0];
         float x[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) x[i] = valid ? pos[(size_t)n * 3 + i] : 0.0f;
 
         // ---------------- encoder: operand cores grp, grp+4, ... of this row
-        for (int kc = grp; kc < all_cores; kc += kGroups) {
+        for (int kc = grp; kc < ((P.knockout & 1) ? 0 : all_cores); kc += kGroups) {
             float fv[8], ft[3][8];
             if (kc < level_cores) {
 #pragma unroll
@@ -170,7 +170,7 @@ k_sdf_fused(FusedParams P, FwdSegs G, const float2* __restrict__ lattice, const 
         // ---------------- MLP: 4 dense layers on the tensor cores
 #pragma unroll 1
         for (int l = 0; l < kNL; l++) {
-            umma::fence_async_smem();
+            if (!(P.knockout & 128)) umma::fence_async_smem();
             umma::fence_before_sync();
             __syncthreads();
             if ((tid & 31) == 0 && warp < S) {
@@ -178,9 +178,11 @@ k_sdf_fused(FusedParams P, FwdSegs G, const float2* __restrict__ lattice, const 
                 // sub-partitions side by side; the mbarrier completes when all S commits have arrived
                 const int s = warp;
                 umma::fence_after_sync();
-                issue_gemm(tmem_base + s * 64, s_a + s * 2 * kATileBytes, s_a + s * 2 * kATileBytes + kATileBytes, s_blob + P.g.w_hi[l],
-                           s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
-                umma::commit(&bars[1]);
+                if (!(P.knockout & 2))
+                    issue_gemm(tmem_base + s * 64, s_a + s * 2 * kATileBytes, s_a + s * 2 * kATileBytes + kATileBytes, s_blob + P.g.w_hi[l],
+                               s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
+                if (P.knockout & 64) umma::mbar_arrive(&bars[1]);      // diagnostics: plain arrive instead of tcgen05.commit
+                else umma::commit(&bars[1]);
             }
             umma::mbar_wait(&bars[1], mma_phase);
             mma_phase ^= 1;
@@ -190,24 +192,38 @@ k_sdf_fused(FusedParams P, FwdSegs G, const float2* __restrict__ lattice, const 
             const bool last = (l == kNL - 1);
             for (int c = grp; c < P.g.Np[l] / 16; c += kGroups) {     // this thread's 16-column chunks
                 float z[16], tz[3][16];
-                umma::tmem_ld16(trow + c * 16, z);
-                if (TAN) {
+                if (P.knockout & 16) {                 // diagnostics: no TMEM reads
 #pragma unroll
-                    for (int j = 0; j < 3; j++) umma::tmem_ld16(trow + (1 + j) * 64 + c * 16, tz[j]);
+                    for (int i = 0; i < 16; i++) { z[i] = 0.f; tz[0][i] = 0.f; tz[1][i] = 0.f; tz[2][i] = 0.f; }
+                } else {
+                    umma::tmem_ld16(trow + c * 16, z);
+                    if (TAN) {
+#pragma unroll
+                        for (int j = 0; j < 3; j++) umma::tmem_ld16(trow + (1 + j) * 64 + c * 16, tz[j]);
+                    }
+                    umma::tmem_ld_wait();
                 }
-                umma::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; i++) z[i] += bias[c * 16 + i];
                 if (!last) {
+                    if (!(P.knockout & 4)) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const GeluEval ge = gelu_eval(z[i]);
-                        if (TAN) {
-                            const float g1 = fmaf(z[i], ge.pdf, ge.cdf);
+                        for (int i = 0; i < 16; i++) {
+                            const GeluEval ge = gelu_eval(z[i]);
+                            if (TAN) {
+                                const float g1 = fmaf(z[i], ge.pdf, ge.cdf);
 #pragma unroll
-                            for (int j = 0; j < 3; j++) tz[j][i] *= g1;
+                                for (int j = 0; j < 3; j++) tz[j][i] *= g1;
+                            }
+                            z[i] *= ge.cdf;
                         }
-                        z[i] *= ge.cdf;
+                    }
+                    if (P.knockout & 8) {             // keep the values alive without the split / store work
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; i++) { acc += z[i]; if (TAN) acc += tz[0][i] + tz[1][i] + tz[2][i]; }
+                        if (acc == 123.456f) s_a[0] = 1;
+                        continue;
                     }
                     store8(s_a, s_a + kATileBytes, row, 2 * c, z);
                     store8(s_a, s_a + kATileBytes, row, 2 * c + 1, z + 8);
@@ -219,7 +235,7 @@ k_sdf_fused(FusedParams P, FwdSegs G, const float2* __restrict__ lattice, const 
                             store8(hi, hi + kATileBytes, row, 2 * c + 1, tz[j] + 8);
                         }
                     }
-                } else if (valid) {
+                } else if (valid && !(P.knockout & 32)) {
                     const int nout = P.g.N[l];
                     if (c == 0) {
                         sdf_out[n] = z[0];
@@ -240,6 +256,264 @@ k_sdf_fused(FusedParams P, FwdSegs G, const float2* __restrict__ lattice, const 
     }
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem_base, S * 64);
+}
+
+// ---------------------------------------------------------------------------------------------- value + tangents, two groups per CTA
+// The kernel above runs its phases in lock step: all 16 warps gather, then all wait for the tensor core, then all run the epilogue
+// (ncu, profiles/README.md: a warp issues 10 % of the time; 28 % long-scoreboard on the MMA mbarrier / gathers, 10 % CTA barrier).
+// Two CTAs per SM would let one CTA's waits be filled by the other's work, but the operand tiles of four streams (128 KB) + the weight
+// blob (57 KB) allow one. Here ONE CTA holds TWO independent groups of 256 threads, each working on its own 64-sample sub-tile
+// (M = 64 MMAs, 64 KB of operand tiles, its own mbarrier, named barrier and 256 TMEM columns) and sharing the resident weights: the
+// groups drift apart and each one's MMA / barrier / gather waits overlap the other's encoder and epilogue work.
+// M = 64 accumulators keep rows 16 q .. 16 q + 15 in TMEM lanes 32 q .. 32 q + 15; they are read with tcgen05.ld.16x256b (m16n8
+// fragment layout, every thread holds useful values) and the next layer's operand cores are written as 4-byte bf16 pairs.
+constexpr int kSub = 64;                        // samples per sub-tile
+constexpr int kSubTileBytes = kSub * 64 * 2;    // one bf16 operand tile [64 x 64]
+constexpr int kGroupThreads = 256;
+constexpr int kStg = 69;                         // row stride (floats) of the output staging tile: 64 value columns max + 3 gradient columns
+
+__device__ __forceinline__ void issue_gemm_m64(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* w_hi,
+                                               const uint8_t* w_lo, int Kp, int Np) {
+    const uint32_t idesc = umma::make_idesc(64, Np, umma::kFmtBF16);
+    const uint32_t sbo_w = (Kp / 8) * kLBO;
+    const uint64_t dah0 = umma::make_desc(umma::smem_u32(a_hi), kLBO, kSBO_A), dal0 = umma::make_desc(umma::smem_u32(a_lo), kLBO, kSBO_A);
+    const uint64_t dwh0 = umma::make_desc(umma::smem_u32(w_hi), kLBO, sbo_w), dwl0 = umma::make_desc(umma::smem_u32(w_lo), kLBO, sbo_w);
+    for (int kk = 0; kk < Kp / 16; kk++) {
+        const uint64_t off = (uint64_t)(kk * ((2 * kLBO) >> 4));
+        umma::mma_bf16(tmem_d, dah0 + off, dwh0 + off, idesc, kk > 0 ? 1u : 0u);
+        umma::mma_bf16(tmem_d, dah0 + off, dwl0 + off, idesc, 1u);
+        umma::mma_bf16(tmem_d, dal0 + off, dwh0 + off, idesc, 1u);
+    }
+}
+// bf16 hi / lo pair of two adjacent columns of one row -> the two operand tiles (4-byte stores; a warp covers whole 128-byte cores)
+__device__ __forceinline__ void store_pair(uint8_t* t_hi, uint8_t* t_lo, int row, int col, float x0, float x1) {
+    uint32_t h, l;
+    umma::split2_bf16(x0, x1, h, l);
+    const int off = (row >> 3) * kSBO_A + (col >> 3) * kLBO + (row & 7) * 16 + (col & 7) * 2;
+    *reinterpret_cast<uint32_t*>(t_hi + off) = h;
+    *reinterpret_cast<uint32_t*>(t_lo + off) = l;
+}
+
+__global__ void __launch_bounds__(2 * kGroupThreads, 1)
+k_sdf_fused_dual(FusedParams P, FwdSegs G, const float2* __restrict__ lattice, const float* __restrict__ scale,
+                 const float* __restrict__ shift, const float* __restrict__ window, const uint8_t* __restrict__ blob) {
+    constexpr int S = 4;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* s_blob = smem;
+    const int tid = threadIdx.x, grp2 = tid >> 8, t = tid & 255;            // group of the CTA, thread inside the group
+    uint8_t* s_a = smem + P.g.total + grp2 * (S * 2 * kSubTileBytes);       // this group's S streams x {hi, lo} x 8 KB
+    LevelC* lc = reinterpret_cast<LevelC*>(smem + P.g.total + 2 * S * 2 * kSubTileBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lc + 1);                    // [0] weights, [1 + g] MMAs of group g, [3] start skew
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wg = t >> 5;                                                   // warp inside the group, 0..7
+    const int row = t & (kSub - 1), eg = t >> 6;                             // encoder: 4 threads per sample row
+    constexpr int kEnc = kGroupThreads / kSub;
+
+    if (tid == 0) {
+        umma::mbar_init(&bars[0], 1);
+        umma::mbar_init(&bars[1], S);
+        umma::mbar_init(&bars[2], S);
+        umma::mbar_init(&bars[3], 1);
+        umma::mbar_fence_init();
+    }
+    for (int i = tid; i < P.L * 3; i += 2 * kGroupThreads) {
+        lc->scale[(i / 3) * 4 + (i % 3)] = scale[i];
+        lc->shift[(i / 3) * 4 + (i % 3)] = shift ? shift[i] : 0.0f;
+    }
+    for (int i = tid; i < P.L; i += 2 * kGroupThreads) lc->window[i] = window ? window[i] : 1.0f;
+    __syncthreads();
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 2 * S * 64);
+    if (tid == 0) {
+        umma::mbar_expect_tx(&bars[0], (uint32_t)P.g.total);
+        umma::bulk_g2s(s_blob, blob, (uint32_t)P.g.total, &bars[0]);
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot + (uint32_t)(grp2 * S * 64);       // this group's 256 columns
+    umma::mbar_wait(&bars[0], 0);
+    uint64_t* mbar = &bars[1 + grp2];
+    uint32_t mma_phase = 0;
+    const int level_cores = P.L / 4, all_cores = P.g.Kp[0] / 8;
+    // epilogue mapping: warp quadrant q = rows 16 q .. 16 q + 15 (TMEM lanes 32 q ..), column half hc = columns 32 hc .. 32 hc + 31
+    const int q = wg & 3, hc = wg >> 2;
+    const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int er0 = q * 16 + (lane >> 2);                                     // rows er0 and er0 + 8 of the sub-tile
+    const int ec0 = hc * 32 + 2 * (lane & 3);                                 // columns ec0 + 8 j + {0, 1}
+
+    const int nsub = G.tile0[2];                                             // in units of 64-sample sub-tiles (see launch_forward)
+    // Two identical groups that start together stay in lock step (every unit is shared fairly), waiting for the tensor core at the same
+    // time. Group 1 therefore starts half a sub-tile late: it waits until group 0 has finished the second layer of its first sub-tile;
+    // from then on one group's MMA / TMEM-read phases meet the other's encoder / GELU / store phases.
+    bool skew_pending = P.skew != 0;
+    if (skew_pending && grp2 == 1 && blockIdx.x * 2 < nsub) { umma::mbar_wait(&bars[3], 0); skew_pending = false; }
+    for (int sub = blockIdx.x * 2 + grp2; sub < nsub; sub += 2 * gridDim.x) {
+        const bool seg1 = sub >= G.tile0[1];
+        const int sub0 = seg1 ? G.tile0[1] : 0, nseg = seg1 ? G.n[1] : G.n[0];
+        const float* __restrict__ pos = seg1 ? G.pos[1] : G.pos[0];
+        float* __restrict__ sdf_out = seg1 ? G.sdf[1] : G.sdf[0];
+        float* __restrict__ grad_out = seg1 ? G.grad[1] : G.grad[0];
+        float* __restrict__ geom_out = seg1 ? G.geom[1] : G.geom[0];
+        const int n = (sub - sub0) * kSub + row;
+        const bool valid = n < nseg;
+        float x[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) x[i] = valid ? pos[(size_t)n * 3 + i] : 0.0f;
+
+        // ---------------- encoder (same arithmetic as k_sdf_fused<true>): operand cores eg, eg + 4, ... of this row
+        for (int kc = eg; kc < all_cores; kc += kEnc) {
+            float fv[8], ft[3][8];
+            if (kc < level_cores) {
+#pragma unroll
+                for (int qq = 0; qq < 4; qq++) {
+                    const int l = kc * 4 + qq;
+                    float cf[3], e[4];
+#pragma unroll
+                    for (int i = 0; i < 3; i++) cf[i] = __fmul_rn(__fadd_rn(x[i], lc->shift[l * 4 + i]), lc->scale[l * 4 + i]);
+                    elevate3(cf, e);
+                    Simplex3 s;
+                    locate3(e, s);
+                    const float2* tab = lattice + (size_t)l * P.T;
+                    float2 v[4];
+#pragma unroll
+                    for (int r = 0; r < 4; r++) v[r] = __ldg(tab + vindex3(s, r, P.cap_mask, (unsigned)P.T));
+                    const float w = lc->window[l];
+                    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 4; r++) { float wr = s.bary[r] * w; a0 = fmaf(v[r].x, wr, a0); a1 = fmaf(v[r].y, wr, a1); }
+                    fv[2 * qq] = a0; fv[2 * qq + 1] = a1;
+                    float2 u[4], Gv[4];
+                    u[0] = make_float2(v[3].x - v[0].x, v[3].y - v[0].y);
+                    u[1] = make_float2(v[2].x - v[3].x, v[2].y - v[3].y);
+                    u[2] = make_float2(v[1].x - v[2].x, v[1].y - v[2].y);
+                    u[3] = make_float2(v[0].x - v[1].x, v[0].y - v[1].y);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int rk = s.rank[i];
+                        Gv[i].x = rk == 0 ? u[0].x : (rk == 1 ? u[1].x : (rk == 2 ? u[2].x : u[3].x));
+                        Gv[i].y = rk == 0 ? u[0].y : (rk == 1 ? u[1].y : (rk == 2 ? u[2].y : u[3].y));
+                    }
+                    const float c0 = 0.25f * w * lc->scale[l * 4], c1 = 0.25f * w * lc->scale[l * 4 + 1], c2 = 0.25f * w * lc->scale[l * 4 + 2];
+                    const float s01x = Gv[0].x + Gv[1].x, s01y = Gv[0].y + Gv[1].y;
+                    ft[0][2 * qq] = c0 * (Gv[0].x - Gv[1].x); ft[0][2 * qq + 1] = c0 * (Gv[0].y - Gv[1].y);
+                    ft[1][2 * qq] = c1 * fmaf(-2.0f, Gv[2].x, s01x); ft[1][2 * qq + 1] = c1 * fmaf(-2.0f, Gv[2].y, s01y);
+                    ft[2][2 * qq] = c2 * fmaf(-3.0f, Gv[3].x, s01x + Gv[2].x); ft[2][2 * qq + 1] = c2 * fmaf(-3.0f, Gv[3].y, s01y + Gv[2].y);
+                }
+            } else {
+                const int c0 = 2 * P.L;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    int c = kc * 8 + i - c0;
+                    float val = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 3; d++) if (c == d && (c0 + c) < P.in_dim) val = x[d] * P.points_scaling;
+                    fv[i] = val;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) ft[j][i] = (c == j && (c0 + c) < P.in_dim) ? P.points_scaling : 0.f;
+                }
+            }
+            store8(s_a, s_a + kSubTileBytes, row, kc, fv);
+#pragma unroll
+            for (int j = 0; j < 3; j++) store8(s_a + (1 + j) * 2 * kSubTileBytes, s_a + (1 + j) * 2 * kSubTileBytes + kSubTileBytes, row, kc, ft[j]);
+        }
+
+        // ---------------- MLP: 4 dense layers, M = 64
+#pragma unroll 1
+        for (int l = 0; l < kNL; l++) {
+            umma::fence_async_smem();
+            umma::fence_before_sync();
+            umma::bar_sync(1 + grp2, kGroupThreads);
+            if (lane == 0 && wg < S) {
+                const int s = wg;
+                umma::fence_after_sync();
+                issue_gemm_m64(tmem_base + s * 64, s_a + s * 2 * kSubTileBytes, s_a + s * 2 * kSubTileBytes + kSubTileBytes, s_blob + P.g.w_hi[l],
+                               s_blob + P.g.w_lo[l], P.g.Kp[l], P.g.Np[l]);
+                umma::commit(mbar);
+            }
+            umma::mbar_wait(mbar, mma_phase);
+            mma_phase ^= 1;
+            umma::fence_after_sync();
+            const float* bias = reinterpret_cast<const float*>(s_blob + P.g.bias[l]);
+            const bool last = (l == kNL - 1);
+            if (hc * 32 < P.g.Np[l]) {                    // this warp's 32 columns exist in this layer (the output layer may be narrower)
+                float z[16], tz[3][16];
+                umma::tmem_ld16x32(tq + hc * 32, z);
+#pragma unroll
+                for (int j = 0; j < 3; j++) umma::tmem_ld16x32(tq + (1 + j) * 64 + hc * 32, tz[j]);
+                umma::tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+#pragma unroll
+                    for (int b = 0; b < 2; b++) {
+                        const float bb = bias[ec0 + 8 * j + b];
+                        z[4 * j + b] += bb; z[4 * j + 2 + b] += bb;
+                    }
+                }
+                if (!last) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const GeluEval ge = gelu_eval(z[i]);
+                        const float g1 = fmaf(z[i], ge.pdf, ge.cdf);
+#pragma unroll
+                        for (int j = 0; j < 3; j++) tz[j][i] *= g1;
+                        z[i] *= ge.cdf;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+#pragma unroll
+                        for (int h = 0; h < 2; h++) {
+                            const int r = er0 + 8 * h, c = ec0 + 8 * j, i = 4 * j + 2 * h;
+                            store_pair(s_a, s_a + kSubTileBytes, r, c, z[i], z[i + 1]);
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                uint8_t* th = s_a + (1 + k) * 2 * kSubTileBytes;
+                                store_pair(th, th + kSubTileBytes, r, c, tz[k][i], tz[k][i + 1]);
+                            }
+                        }
+                    }
+                    if (skew_pending && grp2 == 0 && l == 1) { if (t == 0) umma::mbar_arrive(&bars[3]); skew_pending = false; }
+                } else {
+                    // outputs are staged in shared memory (the operand tiles are dead: the last MMAs completed) and leave as whole rows:
+                    // a fragment thread holds 2 columns of 2 rows, which would be 4-byte stores 128 bytes apart (measured: 8 us of 92)
+                    const int nout = P.g.N[l];
+                    float* stg = reinterpret_cast<float*>(s_a);            // [64][kStg]: sdf | geom (nout - 1) | grad (3)
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int r = er0 + 8 * h;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+#pragma unroll
+                            for (int b = 0; b < 2; b++) {
+                                const int col = ec0 + 8 * j + b;
+                                if (col < nout) stg[r * kStg + col] = z[4 * j + 2 * h + b];
+                            }
+                        }
+                        if (hc == 0 && (lane & 3) == 0) { stg[r * kStg + 64] = tz[0][2 * h]; stg[r * kStg + 65] = tz[1][2 * h]; stg[r * kStg + 66] = tz[2][2 * h]; }
+                    }
+                }
+            }
+        }
+        // ---------------- coalesced copy-out of the sub-tile's rows
+        umma::fence_before_sync();
+        umma::bar_sync(1 + grp2, kGroupThreads);     // staging complete; TMEM reads of this sub-tile done before its next MMAs
+        {
+            const float* stg = reinterpret_cast<const float*>(s_a);
+            const int nout = P.g.N[kNL - 1];
+            const int n0 = (sub - sub0) * kSub;
+            const int rows = min(kSub, nseg - n0);
+            if (t < rows) sdf_out[n0 + t] = stg[t * kStg];
+            if (grad_out) for (int i = t; i < rows * 3; i += kGroupThreads) grad_out[(size_t)n0 * 3 + i] = stg[(i / 3) * kStg + 64 + (i % 3)];
+            if (geom_out) {
+                const int gw = nout - 1;
+                for (int i = t; i < rows * gw; i += kGroupThreads) geom_out[(size_t)n0 * gw + i] = stg[(i / gw) * kStg + 1 + (i % gw)];
+            }
+        }
+        umma::bar_sync(1 + grp2, kGroupThreads);     // the staging area is the next sub-tile's operand tile
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(*tmem_slot, 2 * S * 64);
 }
 
 // ---------------------------------------------------------------------------------------------- fused sphere tracing
@@ -691,6 +965,17 @@ int psdf_sdf_mlp_pack_advance(int in_dim, int hidden, int out_dim, const float* 
     return PSDF_OK;
 }
 
+// kernel choice of the value + tangent forward: 1 = two 64-sample groups per CTA (default), 0 = lock-step 128-sample tiles.
+// Initialised from PSDF_SDF_FWD_DUAL, switchable at run time for A/B measurements (psdf_sdf_forward_variant).
+static int& forward_dual_mode() {
+    static int mode = (getenv("PSDF_SDF_FWD_DUAL") && atoi(getenv("PSDF_SDF_FWD_DUAL")) == 0) ? 0 : 1;
+    return mode;
+}
+int psdf_sdf_forward_variant(int variant) {
+    if (variant == 0 || variant == 1) forward_dual_mode() = variant;
+    return forward_dual_mode();
+}
+
 static int launch_forward(int L, int T, const float* lattice, const float* scale_factor, const float* shift, const float* window,
                           float points_scaling, int hidden, int out_dim, const uint8_t* blob, int nseg, const int* Ns, const float* const* pos,
                           float* const* sdf, float* const* grad, float* const* geom, void* stream) {
@@ -703,6 +988,8 @@ static int launch_forward(int L, int T, const float* lattice, const float* scale
     if (P.in_dim > 64) return PSDF_ERR_UNSUPPORTED;
     static const int free_levels = getenv("PSDF_EXPERIMENT_FREE_LEVELS") ? atoi(getenv("PSDF_EXPERIMENT_FREE_LEVELS")) : 0;
     P.free_levels = free_levels;
+    static const int knockout = getenv("PSDF_EXPERIMENT_KNOCKOUT") ? atoi(getenv("PSDF_EXPERIMENT_KNOCKOUT")) : 0;
+    P.knockout = knockout;
     P.g = make_geom(P.in_dim, hidden, out_dim);
     FwdSegs G;
     int tiles = 0, total = 0;
@@ -724,7 +1011,19 @@ static int launch_forward(int L, int T, const float* lattice, const float* scale
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const float2* lat = reinterpret_cast<const float2*>(lattice);
-    if (tangents) {
+    // value + tangents: two independent 64-sample groups per CTA (k_sdf_fused_dual) unless PSDF_SDF_FWD_DUAL=0 (the lock-step kernel)
+    const bool dual = forward_dual_mode() != 0;
+    static const int skew = getenv("PSDF_SDF_FWD_SKEW") ? atoi(getenv("PSDF_SDF_FWD_SKEW")) : 1;
+    P.skew = skew;
+    if (tangents && dual) {
+        FwdSegs H = G;
+        int subs = 0;
+        for (int i = 0; i < 2; i++) { H.tile0[i] = subs; subs += div_up(G.n[i], kSub); }
+        H.tile0[2] = subs;
+        size_t smem = (size_t)P.g.total + 2 * 4 * 2 * kSubTileBytes + sizeof(LevelC) + 64;
+        { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_fused_dual, 227 * 1024, optin_); }
+        k_sdf_fused_dual<<<min(div_up(subs, 2), sms), 2 * kGroupThreads, smem, ST>>>(P, H, lat, scale_factor, shift, window, blob);
+    } else if (tangents) {
         size_t smem = (size_t)P.g.total + 4 * 2 * kATileBytes + sizeof(LevelC) + 64;
         { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_fused<true>, 227 * 1024, optin_); }
         k_sdf_fused<true><<<min(tiles, sms), kFusedThreads, smem, ST>>>(P, G, lat, scale_factor, shift, window, blob);

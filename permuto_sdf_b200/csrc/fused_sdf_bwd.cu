@@ -172,6 +172,7 @@ k_sdf_fused_backward(FusedParams P, Segments S, const float2* __restrict__ latti
     float* s_gb = reinterpret_cast<float*>(lc + 1);        // 4 x 64 bias-gradient accumulators of this CTA
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_gb + kNL * 64);   // [0] TMA loads, [1] mma, [2] dW mma
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+    float* s_seed = reinterpret_cast<float*>(tmem_slot + 4);   // [128][(out_dim - 1) | 1] upstream d loss / d geom of the tile (coalesced copy)
     float* s_x = reinterpret_cast<float*>(s_X);            // exchange tile abar_0 | tabar_0 : [128][2*Kp0+1] fp32 (aliases X, Y)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -207,17 +208,29 @@ k_sdf_fused_backward(FusedParams P, Segments S, const float2* __restrict__ latti
     long long phase_t0 = out.phase_cycles ? clock64() : 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, first_tile = false) {
         const int seg = tile >= S.tile0[2] ? 2 : (tile >= S.tile0[1] ? 1 : 0);
-        const int n = (tile - S.tile0[seg]) * kTile + row;           // row inside its sample set
-        const bool valid = n < S.n[seg];
-        const float* __restrict__ pos = S.pos[seg];
-        const float* __restrict__ g_sdf = S.g_sdf[seg];
-        const float* __restrict__ g_grad = S.g_grad[seg];
-        const float* __restrict__ g_geom = S.g_geom[seg];
+#define PSDF_SEG(f) (seg == 2 ? S.f[2] : (seg == 1 ? S.f[1] : S.f[0]))     // no dynamic indexing of the parameter struct (local-memory copy)
+        const int seg_tile0 = PSDF_SEG(tile0), seg_n = PSDF_SEG(n);
+        const int n = (tile - seg_tile0) * kTile + row;              // row inside its sample set
+        const bool valid = n < seg_n;
+        const float* __restrict__ pos = PSDF_SEG(pos);
+        const float* __restrict__ g_sdf = PSDF_SEG(g_sdf);
+        const float* __restrict__ g_grad = PSDF_SEG(g_grad);
+        const float* __restrict__ g_geom = PSDF_SEG(g_geom);
+#undef PSDF_SEG
         float x[3], v[3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
             x[i] = valid ? pos[(size_t)n * 3 + i] : 0.0f;
             v[i] = (valid && g_grad) ? g_grad[(size_t)n * 3 + i] : 0.0f;
+        }
+        if (g_geom) {
+            // the tile's rows of the upstream geometric-feature gradient are contiguous: copy them with coalesced loads now (consumed by
+            // the seed phase, several barriers later) instead of 16 scalar loads per thread 128 bytes apart (5 % of the stall samples)
+            const int gw = P.g.N[3] - 1;
+            const int row0 = (tile - seg_tile0) * kTile;
+            const int cnt = min(kTile, seg_n - row0) * gw;
+            const float* __restrict__ src = g_geom + (size_t)row0 * gw;
+            for (int i = tid; i < cnt; i += kBwdThreads) s_seed[(i / gw) * (gw | 1) + (i % gw)] = src[i];
         }
         // ---------------- 1. encoder -> X: operand cores grp, grp+4, ... (4 levels = 8 features = one 16-byte core row)
         for (int kc = grp; kc < K0 / 8; kc += kGroups) {
@@ -301,7 +314,7 @@ k_sdf_fused_backward(FusedParams P, Segments S, const float2* __restrict__ latti
                         float vz = 0.f;
                         if (valid && c < Np / 8) {
                             if (colz == 0) vz = g_sdf ? g_sdf[n] : 0.f;
-                            else if (colz < nout) vz = g_geom ? g_geom[(size_t)n * (nout - 1) + colz - 1] : 0.f;
+                            else if (colz < nout) vz = g_geom ? s_seed[row * ((nout - 1) | 1) + colz - 1] : 0.f;
                         }
                         seed[j][i] = vz;
                     }
@@ -463,7 +476,8 @@ k_sdf_fused_backward(FusedParams P, Segments S, const float2* __restrict__ latti
                 const float w = lc->window[l];
                 const float a0 = xr[2 * l], a1 = xr[2 * l + 1], t0 = xr[K0 + 2 * l], t1 = xr[K0 + 2 * l + 1];
                 float* gtab = grad_lattice + (size_t)l * P.T * 2;
-                const bool aggregate = lc->scale[l * 4] < kAggregateBelowScale;       // warp-uniform (l is)
+                const bool aggregate = lc->scale[l * 4] < kAggregateBelowScale && !(P.knockout & 2);       // warp-uniform (l is)
+                const bool do_red = !(P.knockout & 1);            // diagnostics (PSDF_EXPERIMENT_KNOCKOUT): bit 0 no atomics, bit 1 no aggregation
 #pragma unroll
                 for (int r = 0; r < 4; r++) {
                     unsigned idx = vindex3(s, r, P.cap_mask, (unsigned)P.T);
@@ -473,8 +487,8 @@ k_sdf_fused_backward(FusedParams P, Segments S, const float2* __restrict__ latti
                         unsigned key = valid ? idx : 0xffffffffu;
                         unsigned peers = __match_any_sync(kFull, key);
                         cv = add_peers2(peers, cv, lane);
-                        if (valid && lane == __ffs(peers) - 1) red_v2(gtab + (size_t)idx * 2, cv);
-                    } else if (valid) {
+                        if (valid && lane == __ffs(peers) - 1 && do_red) red_v2(gtab + (size_t)idx * 2, cv);
+                    } else if (valid && (do_red || cv.x == 123.456f)) {
                         red_v2(gtab + (size_t)idx * 2, cv);
                     }
                 }
@@ -547,6 +561,8 @@ static int launch_backward(int nseg, const int* Ns, const float* const* pos, con
     P.in_dim = (L + 2) * 2;
     if (P.in_dim > 64) return PSDF_ERR_UNSUPPORTED;
     P.g = make_geom(P.in_dim, hidden, out_dim);
+    static const int knockout = getenv("PSDF_EXPERIMENT_KNOCKOUT") ? atoi(getenv("PSDF_EXPERIMENT_KNOCKOUT")) : 0;
+    P.knockout = knockout;
     Segments S;
     int tiles = 0, total = 0;
     for (int i = 0; i < kMaxSeg; i++) {
@@ -576,7 +592,7 @@ static int launch_backward(int nseg, const int* Ns, const float* const* pos, con
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t smem = (size_t)P.g.total + 2 * kSetBytes + sizeof(LevelC) + kNL * 64 * sizeof(float) + 64;
+    const size_t smem = (size_t)P.g.total + 2 * kSetBytes + sizeof(LevelC) + kNL * 64 * sizeof(float) + 64 + (size_t)kTile * (size_t)((out_dim - 1) | 1) * sizeof(float);
     if ((size_t)128 * (2 * P.g.Kp[0] + 1) * 4 > (size_t)2 * kSetBytes || smem > 227 * 1024) return PSDF_ERR_UNSUPPORTED;
     { static bool optin_[64]; psdf::psdf_optin_smem(k_sdf_fused_backward, 227 * 1024, optin_); }
     k_sdf_fused_backward<<<min(tiles, sms), kBwdThreads, smem, ST>>>(P, S, reinterpret_cast<const float2*>(lattice), scale_factor, shift, window,

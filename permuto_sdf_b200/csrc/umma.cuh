@@ -82,6 +82,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+// 16 lanes x 32 consecutive 32-bit columns in the layout of an M = 64 accumulator quadrant (rows 16q .. 16q+15 live in lanes
+// 32q .. 32q+15): thread t of the warp gets, for j = 0..3, h = 0..1, b = 0..1,
+//     v[4 j + 2 h + b] = lane (base_lane + t / 4 + 8 h), column (base_col + 8 j + 2 (t % 4) + b)
+// i.e. the m16n8 accumulator fragment repeated over four 8-column blocks -- all 32 threads hold useful data (a 32x32b load of an
+// M = 64 accumulator fills only half of the warp). Validated on B200 by tools/probes/tmem_ld16_probe.cu.
+__device__ __forceinline__ void tmem_ld16x32(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+// named barrier over a subset of the CTA's warps (ids 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // store counterpart: thread t of the warp writes lane (base_lane + t), 16 consecutive columns
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
@@ -102,6 +120,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
