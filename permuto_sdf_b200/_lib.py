@@ -171,16 +171,7 @@ def call(name, *args):
 _KERNELS_PER_CALL = {"psdf_packed_compact_scan": 2, "psdf_vr_combine_uniform_samples_with_imp": 3}
 
 
-def _bwd_kernels(args):
-    """the colour-network backward launches (reverse sweep, dW) once per chunk of 128-sample tiles (csrc/fused_rgb_bwd.cu); the SDF
-    backward is a single kernel (weight gradients formed on chip, csrc/fused_sdf_bwd.cu)"""
-    tiles = (int(args[0]) + 127) // 128
-    chunk = int(os.environ.get("PSDF_BWD_CHUNK_TILES", "0"))
-    chunk = tiles if chunk <= 0 else chunk
-    return 2 * max(1, (tiles + chunk - 1) // chunk)
-
-
-_KERNELS_FN = {"psdf_rgb_fused_backward": _bwd_kernels, "psdf_rgb_fused_backward_acc": _bwd_kernels}
+_KERNELS_FN = {}        # entry point -> launches as a function of its arguments (none at present: every backward is one kernel)
 _UNITS_FN = {"psdf_sdf_fused_forward_multi": lambda a: int(a[10]) + int(a[15]),
              "psdf_sdf_fused_backward_multi": lambda a: int(a[10]) + int(a[15]) + int(a[20])}
 _STATS = None

@@ -4,17 +4,21 @@
 // (permuto_sdf_py/models/models.py:395-414) -- encoding backward, 4 x (GELU backward, 2 GEMMs), normalize / cat backward.
 //
 // Per 128-sample tile (512 threads: row = tid & 127, group = tid >> 7):
-//   1. input tile a_0 (encoder gather + SH + normal + geom) as in the forward;
-//   2. forward recompute, layers 0..2 on the tensor cores; pre-activations z^(0), z^(1), z^(2) STAY in TMEM (128 + 128 + 64
-//      columns); every input tile a_l is spilled (TMA store of the operand tile as it sits in shared memory) for dW;
-//   3. reverse sweep l = 3..0: zbar^(l) tile -> MMA with W_l^T -> abar_l -> zbar^(l-1) = abar_l gelu'(z^(l-1)); the zbar tiles are
-//      spilled the same way; bias gradients = column sums (shuffles + shared atomics);
+//   1. input tile a_0 (encoder gather + SH + normal + geom) as in the forward; a_0 leaves by ONE TMA store (64 KB / tile, re-read from
+//      L2 by the same CTA for dW_0: the only spill);
+//   2. forward recompute, layers 0..2 on the tensor cores; pre-activations z^(0), z^(1), z^(2) STAY in TMEM (128 + 128 + 64 columns);
+//   3. reverse sweep l = 3..0: zbar^(l) tile -> MMA with W_l^T -> abar_l -> zbar^(l-1) = abar_l gelu'(z^(l-1)); while that GEMM runs the
+//      layer's input a_l is rebuilt from the TMEM-resident z^(l-1) (a_0 returns by TMA) and the WEIGHT GRADIENT dW_l = zbar^(l)^T a_l is
+//      formed on the tensor cores from the two tiles as they sit in shared memory: the sample axis is the MMA K dimension and an
+//      operand tile in the K-major core-matrix layout is an MN-major operand for that product (see fused_sdf_bwd.cu). The four
+//      accumulators do not fit beside the z^(l) (320 + 128 work + 416 columns), so dW_l lives in the columns of the z^(l) that is
+//      already dead and is flushed per tile and layer with red.global.add.v4.f32 (160 KB of L2 reductions per tile instead of a
+//      512 KB spill + a second kernel that re-reads it: round 2 measured 257 MB written + 268 MB read per 65 536 samples);
+//      bias gradients = column sums (shuffles + shared atomics);
 //   4. abar_0 -> lattice scatter (warp-aggregated red.global.add.v2.f32), normal -> sdf-gradient, geom gradient.
 // Weights stream per layer through one 64 KB buffer by TMA; the next block is requested as soon as the MMAs that read the
 // current one have retired, so the copy hides behind the epilogue.
-// dW_l = zbar^(l)^T a_l is formed by k_rgb_dw from the spilled tiles: the sample axis is the MMA K dimension and an operand tile
-// in the K-major core-matrix layout is an MN-major operand for that product (see fused_sdf_bwd.cu), M = 128 / 64 accumulators
-// in TMEM, one red.add of the CTA's partial sums at the end.
+// TMEM map: [0,128) z^(0) then dW_0 | [128,256) z^(1) then dW_1 | [256,320) z^(2), [256,384) dW_2, [320,384) dW_3 | [384,512) work.
 #include "fused_common.cuh"
 #include "fused_rgb_common.cuh"
 #include "../../include/psdf_b200.h"
@@ -26,10 +30,23 @@ namespace {
 constexpr int kRgbSpillBytes = 2 * kWTileBytes;      // [hi | lo] of one operand tile
 
 struct RgbSpill {
-    uint8_t* zt[kNL];    // [ntiles][64 KB] zbar^(l) tiles
-    uint8_t* at[kNL];    // [ntiles][64 KB] a_l tiles
+    uint8_t* a0;         // [ntiles][64 KB] input tiles a_0 (written and re-read by the same CTA)
+    float* gW[kNL];      // [N_l, K_l] (+=)
     float* gbias[kNL];   // (+=)
 };
+// dW_l (+)= zbar^(l)^T a_l over the 128 samples of the tile: both tiles consumed as MN-major operands (single thread)
+__device__ __forceinline__ void issue_dw_w(uint32_t tmem_d, const uint8_t* z_hi, const uint8_t* a_hi, int M, int N) {
+    const uint32_t idesc = umma::make_idesc_mn(M, N, umma::kFmtBF16);
+    const uint32_t zh = umma::smem_u32(z_hi), zl = zh + kWTileBytes, ah = umma::smem_u32(a_hi), al = ah + kWTileBytes;
+    for (int kk = 0; kk < kTile / 16; kk++) {                     // 16 samples = 2 eight-row groups
+        const uint32_t ko = kk * 2 * kWSBO;
+        const uint64_t dzh = umma::make_desc(zh + ko, kWSBO, kLBO), dzl = umma::make_desc(zl + ko, kWSBO, kLBO);
+        const uint64_t dah = umma::make_desc(ah + ko, kWSBO, kLBO), dal = umma::make_desc(al + ko, kWSBO, kLBO);
+        umma::mma_bf16(tmem_d, dzh, dah, idesc, kk > 0 ? 1u : 0u);
+        umma::mma_bf16(tmem_d, dzh, dal, idesc, 1u);
+        umma::mma_bf16(tmem_d, dzl, dah, idesc, 1u);
+    }
+}
 
 __global__ void __launch_bounds__(kRgbThreads, 1)
 k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __restrict__ dirs, const float* __restrict__ sdf_grad,
@@ -44,14 +61,15 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
     LevelC* lc = reinterpret_cast<LevelC*>(s_w + 2 * kWTileBytes);
     float* s_bias = reinterpret_cast<float*>(lc + 1);      // 4 x 128
     float* s_gb = s_bias + kNL * 128;                      // 4 x 128 bias-gradient accumulators of this CTA
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_gb + kNL * 128);   // [0] weights, [1] mma
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_gb + kNL * 128);   // [0] weights, [1] forward / reverse MMAs, [2] dW MMAs, [3] a_0 reload
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
     float* s_x = reinterpret_cast<float*>(s_a);            // exchange tile abar_0: [128][K0 + 1] fp32, aliases s_a
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = tid & 127, grp = tid >> 7;
     const int K0 = P.g.Kp[0];
-    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_fence_init(); }
+    if (tid == 0) { umma::mbar_init(&bars[0], 1); umma::mbar_init(&bars[1], 1); umma::mbar_init(&bars[2], 1); umma::mbar_init(&bars[3], 1); umma::mbar_fence_init(); }
+    const bool dw_issuer = (tid == 32);                      // lane 0 of warp 1: the weight-gradient MMAs are issued beside the GEMM chain of thread 0
     load_level_consts(lc, P.L, scale, shift, window, tid, kRgbThreads);
     for (int i = tid; i < kNL * 128; i += kRgbThreads) {
         int l = i >> 7, c = i & 127;
@@ -67,7 +85,9 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
     const uint32_t tmem_z[3] = {tmem_base, tmem_base + 128, tmem_base + 256};
     const uint32_t tmem_work = tmem_base + 384;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t w_phase = 0, mma_phase = 0;
+    uint32_t w_phase = 0, mma_phase = 0, dw_phase = 0, a0_phase = 0;
+    // accumulator columns of dW_l (see the TMEM map above)
+    auto tmem_dw = [tmem_base](int l) -> uint32_t { return tmem_base + (l == 0 ? 0u : (l == 1 ? 128u : (l == 2 ? 256u : 320u))); };
 
     const int ntiles = (P.N + kTile - 1) / kTile;
     if (tid == 0 && blockIdx.x < ntiles) load_layer_weights(s_w, blob, P.g, 0, false, &bars[0]);
@@ -86,10 +106,12 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
             __syncthreads();
             if (tid == 0) {
                 umma::fence_after_sync();
-                umma::bulk_s2g(sp.at[l] + (size_t)tile * kRgbSpillBytes, s_a, kRgbSpillBytes);      // a_l for dW_l
-                umma::bulk_commit();
+                if (l == 0) {        // a_0 leaves as it is (needed again for dW_0 at the end of the reverse sweep)
+                    umma::bulk_s2g(sp.a0 + (size_t)tile * kRgbSpillBytes, s_a, kRgbSpillBytes);
+                    umma::bulk_commit();
+                }
                 issue_gemm_w(tmem_z[l], s_a, s_a + kWTileBytes, s_w, s_w + P.g.Np[l] * P.g.Kp[l] * 2, P.g.Kp[l], P.g.Np[l]);
-                umma::bulk_wait_read0();
+                if (l == 0) umma::bulk_wait_read0();      // s_a is overwritten by this layer's epilogue: the store must have read it
                 umma::commit(&bars[1]);
             }
             umma::mbar_wait(&bars[1], mma_phase);
@@ -118,7 +140,7 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
             const float cs = colsum16(zb, lane, col);
             if (!(lane & 1) && col < 3) atomicAdd(&s_gb[3 * 128 + col], cs);
         }
-        // ---------------- reverse sweep, layers 3..0
+        // ---------------- reverse sweep, layers 3..0: s_z = zbar^(l), s_a = a_l (l = 3: still there from the forward)
 #pragma unroll 1
         for (int l = 3; l >= 0; l--) {
             umma::mbar_wait(&bars[0], w_phase);
@@ -126,17 +148,21 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
             umma::fence_async_smem();
             umma::fence_before_sync();
             __syncthreads();
+            const int Mdw = P.g.Np[l] > 64 ? 128 : 64;
             if (tid == 0) {
                 umma::fence_after_sync();
-                umma::bulk_s2g(sp.zt[l] + (size_t)tile * kRgbSpillBytes, s_z, kRgbSpillBytes);       // zbar^(l) for dW_l
-                if (l == 3) umma::bulk_s2g(sp.at[3] + (size_t)tile * kRgbSpillBytes, s_a, kRgbSpillBytes);   // a_3
-                umma::bulk_commit();
                 // abar_l [128 x Kp_l] = zbar^(l) [128 x Np_l] W_l : B operand = W_l^T stored [Kp_l rows][Np_l]
                 issue_gemm_w(tmem_work, s_z, s_z + kWTileBytes, s_w, s_w + P.g.Np[l] * P.g.Kp[l] * 2, P.g.Np[l], P.g.Kp[l]);
-                umma::bulk_wait_read0();
                 umma::commit(&bars[1]);
             }
-            // while the MMAs run: gelu'(z^(l-1)) of this thread's column chunks from the TMEM-resident pre-activations
+            if (dw_issuer && l == 3) {                    // a_3 | zbar^(3) are both in place
+                umma::fence_after_sync();
+                issue_dw_w(tmem_dw(3), s_z, s_a, Mdw, P.g.Kp[3]);
+                umma::commit(&bars[2]);
+            }
+            // while the MMAs run: gelu'(z^(l-1)) of this thread's column chunks from the TMEM-resident pre-activations, and the layer's
+            // input a_l = gelu(z^(l-1)) back into s_a (its previous content a_(l+1) was last read by dW_(l+1), complete since the
+            // previous step's epilogue waited for it)
             const int Kp = P.g.Kp[l];
             float g1a[16], g1b[16];                       // chunks grp and grp + 4 (Kp <= 128 -> at most two chunks per thread)
             if (l > 0) {
@@ -152,8 +178,29 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
                             const float zz = z[i] + s_bias[(l - 1) * 128 + c * 16 + i];
                             const GeluEval ge = gelu_eval(zz);
                             (j == 0 ? g1a : g1b)[i] = fmaf(zz, ge.pdf, ge.cdf);
+                            z[i] = zz * ge.cdf;
+                        }
+                        if (l < 3) {
+                            store8w(s_a, s_a + kWTileBytes, row, 2 * c, z);
+                            store8w(s_a, s_a + kWTileBytes, row, 2 * c + 1, z + 8);
                         }
                     }
+                }
+            }
+            if (l < 3) {
+                if (l == 0 && tid == 0) {                 // a_0 returns by TMA (its store completed long ago)
+                    umma::bulk_wait0();
+                    umma::mbar_expect_tx(&bars[3], (uint32_t)kRgbSpillBytes);
+                    umma::bulk_g2s(s_a, sp.a0 + (size_t)tile * kRgbSpillBytes, (uint32_t)kRgbSpillBytes, &bars[3]);
+                }
+                umma::fence_async_smem();
+                umma::fence_before_sync();
+                __syncthreads();
+                if (dw_issuer) {
+                    umma::fence_after_sync();
+                    if (l == 0) { umma::mbar_wait(&bars[3], a0_phase); umma::fence_after_sync(); }
+                    issue_dw_w(tmem_dw(l), s_z, s_a, Mdw, Kp);
+                    umma::commit(&bars[2]);
                 }
             }
             umma::mbar_wait(&bars[1], mma_phase);
@@ -163,6 +210,10 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
                 if (l > 0) load_layer_weights(s_w, blob, P.g, l - 1, true, &bars[0]);
                 else if (tile + (int)gridDim.x < ntiles) load_layer_weights(s_w, blob, P.g, 0, false, &bars[0]);
             }
+            // s_z (and, for l = 0, the exchange tile over s_a) may only be written once the dW_l MMAs that read them have completed
+            umma::mbar_wait(&bars[2], dw_phase);
+            dw_phase ^= 1;
+            umma::fence_after_sync();
             if (l > 0) {
 #pragma unroll
                 for (int j = 0; j < 2; j++) {
@@ -192,8 +243,35 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
                     for (int i = 0; i < 16; i++) s_x[row * (K0 + 1) + c * 16 + i] = ab[i];
                 }
             }
+            // ---- flush dW_l of this tile: TMEM -> global (+=). M = 128: accumulator row m in lane m; M = 64: row m in lane
+            // (m / 16) * 32 + m % 16. The four warps of a lane quadrant share the 16-column chunks.
+            {
+                const int q = warp & 3;
+                const int m = Mdw == 128 ? q * 32 + lane : q * 16 + lane;
+                const bool has_row = (Mdw == 128 || lane < 16) && m < P.g.N[l];
+                const int K = P.g.K[l];
+                float* dst_row = sp.gW[l] + (size_t)m * K;
+                const bool vec = (K & 3) == 0 && ((uintptr_t)sp.gW[l] & 15) == 0;
+                for (int c = warp >> 2; c < Kp / 16; c += kRgbThreads / 128) {
+                    float acc[16];
+                    umma::tmem_ld16(tmem_dw(l) + lane_off + c * 16, acc);
+                    umma::tmem_ld_wait();
+                    if (has_row) {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const int k = c * 16 + i;
+                            if (vec && k + 3 < K) red_v4(dst_row + k, acc[i], acc[i + 1], acc[i + 2], acc[i + 3]);
+                            else {
+#pragma unroll
+                                for (int jj = 0; jj < 4; jj++) if (k + jj < K) atomicAdd(dst_row + k + jj, acc[i + jj]);
+                            }
+                        }
+                    }
+                }
+            }
             umma::fence_before_sync();
         }
+        a0_phase ^= 1;
         __syncthreads();
         // ---------------- encoder / tail backward from abar_0
         {
@@ -262,121 +340,16 @@ k_rgb_fused_backward(RgbParams P, const float* __restrict__ pos, const float* __
     if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
 }
 
-// ------------------------------------------------------------------------------------------------ weight gradients
-// stage = (tile, layer, half of the 128 samples): {zbar hi, zbar lo, a hi, a lo} halves, 16 KB each (the first / second 64
-// sample rows of a tile are its first / second 16 KB)
-constexpr int kDwStages = 3;
-constexpr int kDwPiece = kWTileBytes / 2;
-constexpr int kDwStageBytes = 4 * kDwPiece;
-__global__ void __launch_bounds__(128, 1) k_rgb_dw(MlpGeom g, int ntiles, RgbSpill sp, float* __restrict__ gW0, float* __restrict__ gW1,
-                                                  float* __restrict__ gW2, float* __restrict__ gW3) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* ring = smem;
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + kDwStages * kDwStageBytes);
-    uint64_t* empty = full + kDwStages;
-    uint64_t* done = empty + kDwStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int i = 0; i < kDwStages; i++) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
-        umma::mbar_init(done, 1);
-        umma::mbar_fence_init();
-    }
-    __syncthreads();
-    if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
-    umma::fence_before_sync();
-    __syncthreads();
-    umma::fence_after_sync();
-    const uint32_t tmem_base = *tmem_slot;
-    int my_tiles = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) my_tiles++;
-    const int nstage = my_tiles * kNL * 2;            // (tile, layer, half)
-    if (warp == 0 && lane == 0) {
-        for (int i = 0; i < nstage; i++) {
-            const int slot = i % kDwStages, use = i / kDwStages;
-            if (use > 0) umma::mbar_wait(&empty[slot], (use - 1) & 1);
-            const int ti = blockIdx.x + (i / (kNL * 2)) * gridDim.x, l = (i >> 1) % kNL, h = i & 1;
-            uint8_t* dst = ring + slot * kDwStageBytes;
-            const uint8_t* zsrc = sp.zt[l] + (size_t)ti * kRgbSpillBytes + h * kDwPiece;
-            const uint8_t* asrc = sp.at[l] + (size_t)ti * kRgbSpillBytes + h * kDwPiece;
-            umma::mbar_expect_tx(&full[slot], (uint32_t)kDwStageBytes);
-            umma::bulk_g2s(dst, zsrc, kDwPiece, &full[slot]);
-            umma::bulk_g2s(dst + kDwPiece, zsrc + kWTileBytes, kDwPiece, &full[slot]);
-            umma::bulk_g2s(dst + 2 * kDwPiece, asrc, kDwPiece, &full[slot]);
-            umma::bulk_g2s(dst + 3 * kDwPiece, asrc + kWTileBytes, kDwPiece, &full[slot]);
-        }
-    } else if (warp == 1 && lane == 0) {
-        for (int i = 0; i < nstage; i++) {
-            const int slot = i % kDwStages, use = i / kDwStages;
-            umma::mbar_wait(&full[slot], use & 1);
-            umma::fence_after_sync();
-            const int l = (i >> 1) % kNL;
-            const int M = g.Np[l] > 64 ? 128 : 64;
-            const uint32_t idesc = umma::make_idesc_mn(M, g.Kp[l], umma::kFmtBF16);
-            const uint32_t zh = umma::smem_u32(ring + slot * kDwStageBytes), zl = zh + kDwPiece, ah = zl + kDwPiece, al = ah + kDwPiece;
-            const uint32_t d = tmem_base + l * 128;
-            for (int kk = 0; kk < 4; kk++) {                         // 64 samples = 4 K-steps of 16
-                const uint32_t ko = kk * 2 * kWSBO;
-                const uint64_t dzh = umma::make_desc(zh + ko, kWSBO, kLBO), dzl = umma::make_desc(zl + ko, kWSBO, kLBO);
-                const uint64_t dah = umma::make_desc(ah + ko, kWSBO, kLBO), dal = umma::make_desc(al + ko, kWSBO, kLBO);
-                umma::mma_bf16(d, dzh, dah, idesc, (i >= kNL * 2 || (i & 1) || kk > 0) ? 1u : 0u);
-                umma::mma_bf16(d, dzh, dal, idesc, 1u);
-                umma::mma_bf16(d, dzl, dah, idesc, 1u);
-            }
-            umma::commit(&empty[slot]);
-        }
-        umma::commit(done);
-    }
-    __syncwarp();
-    umma::mbar_wait(done, 0);
-    umma::fence_after_sync();
-    float* gW[kNL] = {gW0, gW1, gW2, gW3};
-    if (nstage > 0) {
-        for (int l = 0; l < kNL; l++) {
-            const bool m128 = g.Np[l] > 64;
-            // M = 128: accumulator row m in lane m; M = 64: row m in lane (m / 16) * 32 + m % 16
-            const int m = m128 ? warp * 32 + lane : warp * 16 + lane;
-            const bool has_row = (m128 || lane < 16) && m < g.N[l];
-            for (int c = 0; c < g.Kp[l] / 16; c++) {
-                float v[16];
-                umma::tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + l * 128 + c * 16, v);
-                umma::tmem_ld_wait();
-                if (has_row) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const int k = c * 16 + i;
-                        if (k < g.K[l]) atomicAdd(gW[l] + (size_t)m * g.K[l] + k, v[i]);
-                    }
-                }
-            }
-        }
-    }
-    umma::fence_before_sync();
-    __syncthreads();
-    if (warp == 0) umma::tmem_dealloc(tmem_base, 512);
-}
-
 #define ST ((cudaStream_t)stream)
 }  // namespace
 
 extern "C" {
 
-// chunked like the SDF backward (fused_sdf_bwd.cu): one wave of tiles per chunk so that the dW kernel reads the spill from L2
-static int rgb_bwd_chunk_tiles(int ntiles) {
-    static int chunk = -1;
-    if (chunk < 0) {
-        const char* e = getenv("PSDF_BWD_CHUNK_TILES");
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        chunk = e ? atoi(e) : 0;      // default: one chunk (measured on B200: per-wave chunks cost more in drain / refill than L2 hits give back)
-        (void)sms;
-    }
-    return (chunk <= 0 || chunk > ntiles) ? ntiles : chunk;
-}
+// workspace: the input operand tiles a_0 (64 KB per 128-sample tile), written by TMA store in the forward recompute and read back by the
+// same CTA for the first layer's weight gradient
 long long psdf_rgb_fused_backward_workspace_bytes(int N) {
     const int ntiles = div_up(N > 0 ? N : 1, kTile);
-    return (long long)2 * kNL * rgb_bwd_chunk_tiles(ntiles) * kRgbSpillBytes;
+    return (long long)ntiles * kRgbSpillBytes;
 }
 
 static int rgb_backward_impl(int N, int L, int T, const float* pos, const float* dirs, const float* sdf_grad, const float* geom, int geom_dim,
@@ -392,34 +365,19 @@ static int rgb_backward_impl(int N, int L, int T, const float* pos, const float*
     if ((size_t)128 * (P.g.Kp[0] + 1) * 4 > (size_t)2 * kWTileBytes) return PSDF_ERR_UNSUPPORTED;
     RgbSpill sp;
     float* b[kNL] = {gb0, gb1, gb2, gb3};
+    float* w[kNL] = {gW0, gW1, gW2, gW3};
+    for (int l = 0; l < kNL; l++) { sp.gbias[l] = b[l]; sp.gW[l] = w[l]; }
+    sp.a0 = workspace;
     const int ntiles = div_up(N, kTile);
-    const int chunk = rgb_bwd_chunk_tiles(ntiles);
-    for (int l = 0; l < kNL; l++) {
-        sp.zt[l] = workspace + (size_t)(2 * l) * chunk * kRgbSpillBytes;
-        sp.at[l] = workspace + (size_t)(2 * l + 1) * chunk * kRgbSpillBytes;
-        sp.gbias[l] = b[l];
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t smem = (size_t)6 * kWTileBytes + sizeof(LevelC) + 2 * kNL * 128 * sizeof(float) + 64;
     // per device: set on every call (a second GPU needs its own opt-in)
     { static bool optin_[64]; psdf::psdf_optin_smem(k_rgb_fused_backward, 227 * 1024, optin_); }
-    { static bool optin_[64]; psdf::psdf_optin_smem(k_rgb_dw, 227 * 1024, optin_); }
-    const size_t smem_dw = (size_t)kDwStages * kDwStageBytes + 128;
-    for (int t0 = 0; t0 < ntiles; t0 += chunk) {
-        const int nt = min(chunk, ntiles - t0);
-        const size_t r0 = (size_t)t0 * kTile;
-        RgbParams Pc = P;
-        Pc.N = (int)min((size_t)nt * kTile, (size_t)N - r0);
-        k_rgb_fused_backward<<<min(nt, sms), kRgbThreads, smem, ST>>>(Pc, pos + r0 * 3, dirs + r0 * 3, sdf_grad + r0 * 3, geom + r0 * kGeomDim,
-                                                                      reinterpret_cast<const float2*>(lattice), scale_factor, shift, window,
-                                                                      blob, g_out + r0 * 3, grad_lattice, g_sdf_grad ? g_sdf_grad + r0 * 3 : nullptr,
-                                                                      g_geom ? g_geom + r0 * kGeomDim : nullptr, sp);
-        PSDF_CHECK_LAUNCH();
-        k_rgb_dw<<<min(nt, sms), 128, smem_dw, ST>>>(P.g, nt, sp, gW0, gW1, gW2, gW3);
-        PSDF_CHECK_LAUNCH();
-    }
+    k_rgb_fused_backward<<<min(ntiles, sms), kRgbThreads, smem, ST>>>(P, pos, dirs, sdf_grad, geom, reinterpret_cast<const float2*>(lattice),
+                                                                      scale_factor, shift, window, blob, g_out, grad_lattice, g_sdf_grad, g_geom, sp);
+    PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }
 

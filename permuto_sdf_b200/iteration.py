@@ -71,7 +71,7 @@ class DirectIteration:
         lib = load_library()
         dims = [fr.in_dim] + fr.h + [3]
         sizes = [dims[l + 1] * dims[l] for l in range(4)]
-        gweff = torch.zeros(sum(sizes), device=dev)          # d loss / d W_eff: accumulated by k_rgb_dw, reset by psdf_lipschitz_backward4
+        gweff = torch.zeros(sum(sizes), device=dev)          # d loss / d W_eff: accumulated by k_rgb_fused_backward (per-tile reductions), reset by psdf_lipschitz_backward4
         offs = [0, sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]]
         ws = dict(
             sdf=f(N, 1), grad=f(N, 3), geom=f(N, fs.out_dim - 1), x_raw=f(N, 3),
