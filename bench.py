@@ -204,7 +204,9 @@ def run_ours(args):
         # e2e: the step's inputs start in pinned host memory; otherwise they are device resident
         pix, img = (pix_host[i], img_host[i]) if e2e else (pix_dev[i], img_dev[i])
         dp = tr._dp is not None
-        loss = tr.step_from_reel(reel, pix, img, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1 or dp))
+        # device-resident indices were materialised before the synchronize() that precedes the timed region (inputs_ready): the
+        # parameter-free head of the iteration may then start beside the previous optimizer step
+        loss = tr.step_from_reel(reel, pix, img, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1 or dp), inputs_ready=not e2e)
         if world > 1 and not dp:
             # legacy path (PSDF_DP_MODE=legacy): one blocking NCCL all-reduce of the flat gradient buffer between the two graphs
             dist.all_reduce(tr.optimizer.flat_grad if flat is None else flat.flat, op=dist.ReduceOp.SUM)

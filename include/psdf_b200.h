@@ -354,10 +354,11 @@ int psdf_sphere_rand_points_inside_u01(int n, float radius, const float* u01, fl
 /* psdf_adamw_step over up to 8 parameter groups in one launch: device-resident step count, per-group hyper_dev [2] = {lr, weight_decay};
  * gradients scaled by grad_scale and reset to zero. n_l % 4 == 0, 16-byte aligned pointers. n and the five tables of device addresses
  * (one entry per group) are HOST arrays. The step used is step_dev[0] + step_offset (step_offset = 1: the counter is advanced afterwards
- * by psdf_sdf_mlp_pack_advance). */
+ * by psdf_sdf_mlp_pack_advance). leave_room != 0: few resident blocks with more loads in flight each, so that kernels of another
+ * stream (the next iteration's occupancy sampling) can be co-resident with the sweep. */
 int psdf_adamw_multi_step(int n_groups, const long long* n, const uint64_t* param, const uint64_t* grad, const uint64_t* exp_avg,
                           const uint64_t* exp_avg_sq, const uint64_t* hyper_dev, float beta1, float beta2, float eps, const int* step_dev,
-                          int step_offset, float grad_scale, void* stream);
+                          int step_offset, float grad_scale, int leave_room, void* stream);
 
 /* ---------------------------------------------------------------- dense fused AdamW (torch.optim.AdamW / apex FusedAdam math,
  * train_permuto_sdf.py:293-304); step >= 1 is the incremented step count; grad is multiplied by grad_scale and, when

@@ -8,6 +8,7 @@
 //                       exp(-100 |sdf|), Lipschitz bound), the weighted total and the off-surface gradient seed                      1 for ~30
 //   k_rand_points_u01   Sphere.rand_points_inside from one uniform draw [3,n]                                                          1 for 3
 //   k_adamw_multi       AdamW over several parameter groups in one launch (optim.cu k_adamw per group otherwise)
+#include <cstdlib>
 #include "fused_rgb_common.cuh"
 #include "../../include/psdf_b200.h"
 
@@ -242,21 +243,23 @@ struct AdamGroups {
     float* p[8]; float* g[8]; float* m[8]; float* v[8];
     const float* hyper_dev[8];    // [2] {lr, weight_decay} per group
 };
+template <int U>
 __global__ void __launch_bounds__(256)
 k_adamw_multi(AdamGroups A, float beta1, float beta2, float eps, const int* __restrict__ step_dev, int step_offset, float grad_scale) {
-    // same arithmetic, in the same order, as optim.cu k_adamw (device-resident step count and hyper-parameters)
+    // same arithmetic, in the same order, as optim.cu k_adamw (device-resident step count and hyper-parameters). U float4 quadruples
+    // {p, g, m, v} per thread and iteration: 4 U 16-byte loads in flight before the first use, so that FEW resident blocks saturate HBM
     const float t = (float)(step_dev[0] + step_offset);
     const float bias_c1 = 1.0f - powf(beta1, t);
     const float bias_c2_sqrt = sqrtf(1.0f - powf(beta2, t));
     const long long total = A.off4[A.n_groups];
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
-        float4 P[2], G[2], M[2], V[2];
-        long long j[2];
-        int gi[2];
-        bool ok[2];
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        float4 P[U], G[U], M[U], V[U];
+        long long j[U];
+        int gi[U];
+        bool ok[U];
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
+        for (int q = 0; q < U; q++) {
             const long long i = i0 + q * stride;
             ok[q] = i < total;
             gi[q] = 0; j[q] = 0;
@@ -268,7 +271,7 @@ k_adamw_multi(AdamGroups A, float beta1, float beta2, float eps, const int* __re
             M[q] = reinterpret_cast<float4*>(A.m[g])[j[q]]; V[q] = reinterpret_cast<float4*>(A.v[g])[j[q]];
         }
 #pragma unroll
-        for (int q = 0; q < 2; q++) {
+        for (int q = 0; q < U; q++) {
             if (!ok[q]) continue;
             const float lr = A.hyper_dev[gi[q]][0], wd = A.hyper_dev[gi[q]][1];
             const float decay = 1.0f - lr * wd;
@@ -391,7 +394,7 @@ int psdf_sphere_rand_points_inside_u01(int n, float radius, const float* u01, fl
 // are scaled by grad_scale and reset to zero). n_l % 4 == 0, pointers 16-byte aligned. The step is step_dev[0] + step_offset.
 int psdf_adamw_multi_step(int n_groups, const long long* n, const uint64_t* param, const uint64_t* grad, const uint64_t* exp_avg,
                           const uint64_t* exp_avg_sq, const uint64_t* hyper_dev, float beta1, float beta2, float eps, const int* step_dev,
-                          int step_offset, float grad_scale, void* stream) {
+                          int step_offset, float grad_scale, int leave_room, void* stream) {
     if (n_groups < 1 || n_groups > 8 || !step_dev) return PSDF_ERR_ARG;
     AdamGroups A;
     A.n_groups = n_groups;
@@ -408,8 +411,19 @@ int psdf_adamw_multi_step(int n_groups, const long long* n, const uint64_t* para
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long blocks = (off + 255) / 256;
-    k_adamw_multi<<<(unsigned)(blocks < (long long)sms * 8 ? blocks : (long long)sms * 8), 256, 0, ST>>>(A, beta1, beta2, eps, step_dev, step_offset, grad_scale);
+    // Persistent grid-stride blocks. leave_room = 0: 8 blocks of 256 threads per SM, 2 float4 quadruples in flight per thread (104 us for
+    // the 16.9 M parameters of the bench, 72 % of the measured copy peak). leave_room != 0: 2 blocks per SM with 4 quadruples in flight
+    // (136 us alone) -- most of the register file stays free, so that the next iteration's ray generation / occupancy sampling kernels,
+    // replayed on another stream while this sweep runs (Trainer._step_graphed), are co-resident instead of waiting for the sweep to drain:
+    // measured 1.215 vs 1.24-1.26 ms per iteration (profiles/README.md; 3 or 4 blocks per SM and a high-priority stream are worse).
+    static const int per_sm_env = getenv("PSDF_ADAMW_BLOCKS_PER_SM") ? atoi(getenv("PSDF_ADAMW_BLOCKS_PER_SM")) : 0;
+    static const int unroll_env = getenv("PSDF_ADAMW_UNROLL") ? atoi(getenv("PSDF_ADAMW_UNROLL")) : 0;
+    const int per_sm = per_sm_env > 0 ? per_sm_env : (leave_room ? 2 : 8);
+    const int unroll = unroll_env > 0 ? unroll_env : (leave_room ? 4 : 2);
+    const long long blocks = (off + 255) / 256, cap = (long long)sms * per_sm;
+    const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    if (unroll >= 4) k_adamw_multi<4><<<grid, 256, 0, ST>>>(A, beta1, beta2, eps, step_dev, step_offset, grad_scale);
+    else k_adamw_multi<2><<<grid, 256, 0, ST>>>(A, beta1, beta2, eps, step_dev, step_offset, grad_scale);
     PSDF_CHECK_LAUNCH();
     return PSDF_OK;
 }

@@ -104,8 +104,22 @@ class DirectIteration:
         return ws["scal"]
 
     # ------------------------------------------------------------------------------------------ the iteration
-    def run(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, it):
-        """forward + losses + backward; parameter gradients land in the optimizer's .grad views. -> detached 0-d loss tensor"""
+    def sample_uniform(self, ray_origins, ray_dirs):
+        """Part A of the iteration: bounding-sphere intersection and occupancy-grid sampling (train_permuto_sdf.py:111-135). It reads no
+        network parameter, so under CUDA-graph replay it is a graph of its own that runs beside the previous iteration's optimizer step
+        (Trainer._step_graphed). One sphere intersection serves sampling, resampling and the hit mask."""
+        tr = self.tr
+        hp = tr.hp
+        with torch.no_grad():
+            _, t_entry, _, t_exit, does_hit = tr.aabb.ray_intersection(ray_origins, ray_dirs)
+            jitter = tr.model_sdf.training if getattr(hp, "jitter_samples", None) is None else bool(hp.jitter_samples)
+            fg = tr.occupancy_grid.compute_samples_in_occupied_regions(ray_origins, ray_dirs, t_entry, t_exit, hp.min_dist_between_samples,
+                                                                       hp.max_nr_samples_per_ray, jitter).compact_to_valid_samples()
+        return dict(t_exit=t_exit, does_hit=does_hit, fg=fg, jitter=jitter)
+
+    def run(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, it, pre=None):
+        """forward + losses + backward; parameter gradients land in the optimizer's .grad views. -> detached 0-d loss tensor.
+        pre: result of sample_uniform() for these rays when it already ran (as its own graph)"""
         from .train import importance_sampling_sdf_model
         tr = self.tr
         hp = tr.hp
@@ -117,12 +131,10 @@ class DirectIteration:
         # Python control flow on the iteration (narrows the validity range of a captured graph, DeviceIter)
         curv_on = it < hp.iter_finish_reduce_curv
         lip_on = it >= hp.iter_start_reduce_curv
+        if pre is None:
+            pre = self.sample_uniform(ray_origins, ray_dirs)
+        t_exit, does_hit, fg, jitter = pre["t_exit"], pre["does_hit"], pre["fg"], pre["jitter"]
         with torch.no_grad():
-            # ---------------- sampling (train_permuto_sdf.py:111-135): one sphere intersection serves sampling, resampling and the hit mask
-            _, t_entry, _, t_exit, does_hit = tr.aabb.ray_intersection(ray_origins, ray_dirs)
-            jitter = m_sdf.training if getattr(hp, "jitter_samples", None) is None else bool(hp.jitter_samples)
-            fg = tr.occupancy_grid.compute_samples_in_occupied_regions(ray_origins, ray_dirs, t_entry, t_exit, hp.min_dist_between_samples,
-                                                                       hp.max_nr_samples_per_ray, jitter).compact_to_valid_samples()
             if fg.samples_pos.shape[0] != 0:
                 fg = importance_sampling_sdf_model(m_sdf, fg, ray_origins, ray_dirs, t_exit, it, hp.nr_samples_imp_sampling, jitter=jitter)
             n_mean = None

@@ -169,11 +169,12 @@ class FusedAdamW:
         return dict(key=key, k=k, n=n, p=tab(self.flat_param), g=tab(self.flat_grad), m=tab(self.exp_avg), v=tab(self.exp_avg_sq), h=hyper)
 
     @torch.no_grad()
-    def step(self, grad_scale=1.0, groups=None, advance=True, defer_counter=False):
+    def step(self, grad_scale=1.0, groups=None, advance=True, defer_counter=False, leave_room=False):
         """groups: indices of the param groups to sweep (None: all). advance=False: a second call of the same optimizer step (the
         data-parallel path steps the colour hash table while the other gradients are still being all-reduced).
         defer_counter=True (device-resident step count, all groups): ONE launch sweeps every group with step = step_dev + 1 and the
-        counter itself is advanced by the caller's psdf_sdf_mlp_pack_advance (Trainer: the re-pack that closes the iteration)."""
+        counter itself is advanced by the caller's psdf_sdf_mlp_pack_advance (Trainer: the re-pack that closes the iteration).
+        leave_room: few resident blocks, so that kernels of another stream can run beside the sweep (see csrc/iter_glue.cu)."""
         if self._peer is not None:
             return self._peer_step(grad_scale, advance)
         if advance:
@@ -190,7 +191,7 @@ class FusedAdamW:
                 mt = self._multi = self._multi_tables()
             call("psdf_adamw_multi_step", mt["k"], ctypes.addressof(mt["n"]), ctypes.addressof(mt["p"]), ctypes.addressof(mt["g"]),
                  ctypes.addressof(mt["m"]), ctypes.addressof(mt["v"]), ctypes.addressof(mt["h"]), b1, b2, self.eps, self.step_dev, 1,
-                 float(grad_scale))
+                 float(grad_scale), 1 if leave_room else 0)
             self._clean = True
             return True
         step_dev = None

@@ -425,11 +425,12 @@ class Trainer:
         fr = self.fixed_random
         return fr[name] if (fr is not None and name in fr) else fn()
 
-    def forward_backward(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal):
+    def forward_backward(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal, pre=None):
         """losses + backward of one iteration; parameter gradients are ACCUMULATED into .grad (the caller has run
-        optimizer.zero_grad(); outside any graph capture). -> detached loss"""
+        optimizer.zero_grad(); outside any graph capture). -> detached loss. pre: DirectIteration.sample_uniform() of these rays when
+        it already ran as its own graph"""
         if self._direct is not None:
-            loss = self._direct.run(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal)
+            loss = self._direct.run(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal, pre=pre)
             if loss is not None:
                 return loss
         loss = self.losses(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal)
@@ -651,7 +652,10 @@ class Trainer:
         opt.step_dev = torch.full((1,), opt.step_count, dtype=torch.int32, device=dev)
         opt.sync_hyper()
         self._cg = dict(warm=int(warmup_steps), fb=None, opt={}, occ=None, it_dev=torch.zeros((), device=dev), it_host=None,
-                        stream=torch.cuda.Stream(device=dev), launches=0)
+                        stream=torch.cuda.Stream(device=dev), launches=0,
+                        # the parameter-free head of the iteration (ray generation + occupancy sampling) is a graph of its own on this stream:
+                        # it runs beside the previous iteration's optimizer step (see _step_graphed)
+                        stream_a=torch.cuda.Stream(device=dev), ev_fb=None, split=(self._direct is not None))
 
     def disable_cuda_graph(self):
         """back to eager iterations with exactly-sized containers (host sync per compaction, like the reference)"""
@@ -671,7 +675,7 @@ class Trainer:
             cg["it_dev"].fill_(float(self.iter_nr))
             cg["it_host"] = self.iter_nr
 
-    def step_from_reel(self, tensor_reel, pixel_indices, image_indices, update_occupancy=None, optimizer_step=True):
+    def step_from_reel(self, tensor_reel, pixel_indices, image_indices, update_occupancy=None, optimizer_step=True, inputs_ready=False):
         """one iteration from (pixel, image) indices into a TensorReel: ray generation (PermutoSDF.rays_from_reel_indices) + step.
         Under CUDA-graph replay the indices are the graph's inputs -- host (pinned) or device int32 tensors, copied straight into the
         static buffers -- and the ray-generation kernel is part of the replayed graph."""
@@ -682,9 +686,11 @@ class Trainer:
                 o, d, gt, gm, idx = make_rays(pixel_indices.to(dev, non_blocking=True), image_indices.to(dev, non_blocking=True))
             return self.step(o, d, gt, gm, idx, update_occupancy=update_occupancy, optimizer_step=optimizer_step)
         self.model_sdf.train(); self.model_rgb.train()
-        return self._step_graphed(pixel_indices, image_indices, None, None, None, update_occupancy, optimizer_step, make_rays=make_rays)
+        return self._step_graphed(pixel_indices, image_indices, None, None, None, update_occupancy, optimizer_step, make_rays=make_rays,
+                                  inputs_ready=inputs_ready)
 
-    def _step_graphed(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy, optimizer_step, make_rays=None):
+    def _step_graphed(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy, optimizer_step, make_rays=None,
+                      inputs_ready=False):
         cg = self._cg
         it = self.iter_nr
         self._sync_device_iter()
@@ -714,9 +720,28 @@ class Trainer:
         else:
             if not valid:
                 fb = cg["fb"] = self._capture_forward_backward(inputs, shapes, it, make_rays)
-            for dst, src in zip(fb["static"], inputs):
-                if dst is not None:
-                    dst.copy_(src, non_blocking=True)
+            if fb.get("graph_a") is not None:
+                # Two graphs. A (inputs -> rays -> occupancy samples) reads no network parameter: it is replayed on its own stream and only
+                # waits for the END OF THE PREVIOUS ITERATION'S forward/backward graph (whose kernels read the containers A overwrites) and
+                # occupancy refresh -- not for the previous optimizer step, which is still running on the current stream: the HBM-bound
+                # AdamW sweep and the latency-bound occupancy march overlap. B (everything else) follows on the current stream.
+                side = cg["stream_a"]
+                if cg["ev_fb"] is not None:
+                    side.wait_event(cg["ev_fb"])
+                else:
+                    side.wait_stream(cur)
+                if not inputs_ready and any(t is not None and t.is_cuda for t in inputs):
+                    side.wait_stream(cur)                    # device inputs may have been produced on the current stream just now
+                with torch.cuda.stream(side):
+                    for dst, src in zip(fb["static"], inputs):
+                        if dst is not None:
+                            dst.copy_(src, non_blocking=True)
+                    fb["graph_a"].replay()
+                cur.wait_stream(side)
+            else:
+                for dst, src in zip(fb["static"], inputs):
+                    if dst is not None:
+                        dst.copy_(src, non_blocking=True)
             self.optimizer.zero_grad(set_to_none=False)     # no-op unless a previous iteration skipped its optimizer step
             fb["graph"].replay()
             self.last = fb["last"]
@@ -730,6 +755,10 @@ class Trainer:
             self._update_occupancy_graphed(it)
         if self.hp.adaptive_nr_rays:
             self.adapt_nr_rays(int(self.last["nr_samples_dev"].item()))     # the reference's loop reads the count every iteration too
+        if cg.get("split"):
+            ev = cg["ev_fb"] if cg["ev_fb"] is not None else torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())          # forward/backward (+ occupancy refresh) of this iteration are queued up to here
+            cg["ev_fb"] = ev
         self.apply_schedules(it)
         if optimizer_step:
             self.optimizer_step()
@@ -775,17 +804,32 @@ class Trainer:
         from ._lib import stats_begin, stats_end
         stats_begin(with_events=False)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, stream=cg["stream"]):
-            args = static
-            if make_rays is not None:
-                with torch.no_grad():
-                    args = make_rays(*static)
-            out = self.forward_backward(*args, dit)
-            self._dp_join_backward()
+        g_a = None
+        if cg.get("split") and self._direct is not None:
+            # graph A: inputs -> rays -> occupancy samples (no network parameter read); graph B: the rest, sharing A's memory pool
+            g_a = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_a, stream=cg["stream_a"]):
+                args = static
+                if make_rays is not None:
+                    with torch.no_grad():
+                        args = make_rays(*static)
+                pre = self._direct.sample_uniform(args[0], args[1])
+            with torch.cuda.graph(g, stream=cg["stream"], pool=g_a.pool()):
+                out = self.forward_backward(*args, dit, pre=pre)
+                self._dp_join_backward()
+        else:
+            with torch.cuda.graph(g, stream=cg["stream"]):
+                args = static
+                if make_rays is not None:
+                    with torch.no_grad():
+                        args = make_rays(*static)
+                out = self.forward_backward(*args, dit)
+                self._dp_join_backward()
         _, launches, _ = stats_end()
         dp_rgb = bool(self._dp.pop("rgb_reduced", False)) if getattr(self, "_dp", None) is not None else False
         cg["occ"] = None               # the refresh graph reads tensors of the iteration graph (last inv_s): capture it again
-        return dict(graph=g, static=static, loss=out, last=self.last, shapes=shapes, lo=dit.lo, hi=dit.hi, launches=launches,
+        cg["ev_fb"] = None             # the first replay waits for everything queued so far
+        return dict(graph=g, graph_a=g_a, static=static, loss=out, last=self.last, shapes=shapes, lo=dit.lo, hi=dit.hi, launches=launches,
                     dp_rgb_reduced=dp_rgb)
 
     def _optimizer_step_graphed(self, grad_scale, allreduce=False):
@@ -808,7 +852,7 @@ class Trainer:
                     import torch.distributed as dist
                     dist.all_reduce(self.optimizer.flat_grad, op=dist.ReduceOp.SUM)
                 # every group in one launch; the step counter is advanced by the re-pack below (2 launches instead of 7)
-                deferred = self.optimizer.step(grad_scale=grad_scale, defer_counter=True) is True
+                deferred = self.optimizer.step(grad_scale=grad_scale, defer_counter=True, leave_room=bool(cg.get("split"))) is True
             if deferred:
                 self.model_sdf.fused.repack(advance=(self.optimizer.step_dev, cg["it_dev"]))
             else:

@@ -197,9 +197,21 @@ def test_glue_kernels_match_the_per_op_kernels(cuda):
     tp, tg, tm, tv = tab(P), tab(Gd), tab(M), tab(V)
     th = (ctypes.c_uint64 * k)(*[hyper.data_ptr() + 8 * i for i in range(k)])
     call("psdf_adamw_multi_step", k, ctypes.addressof(nn), ctypes.addressof(tp), ctypes.addressof(tg), ctypes.addressof(tm),
-         ctypes.addressof(tv), ctypes.addressof(th), 0.9, 0.99, 1e-15, step, 1, 0.5)
+         ctypes.addressof(tv), ctypes.addressof(th), 0.9, 0.99, 1e-15, step, 1, 0.5, 0)
     for i in range(k):
         assert torch.equal(P[i], Pa[i]) and torch.equal(M[i], Ma[i]) and torch.equal(V[i], Va[i]) and float(Gd[i].abs().max()) == 0.0
+    # the low-occupancy variant (4 quadruples in flight per thread, 2 blocks per SM) computes the same thing
+    P2, G2, M2, V2 = [[t.clone() for t in X] for X in (Pa, Ga, Ma, Va)]
+    for i, n in enumerate(ns):
+        G2[i].copy_(torch.randn(n, device=dev)); Ga[i].copy_(G2[i])
+        call("psdf_adamw_step", n, Pa[i], Ga[i], Ma[i], Va[i], 0.0, 0.9, 0.99, 1e-15, 0.0, 8, torch.tensor([8], dtype=torch.int32, device=dev),
+             hyper[i], 0.5, 1)
+    t2 = lambda X: (ctypes.c_uint64 * k)(*[t.data_ptr() for t in X])
+    a, b_, c_, d_ = t2(P2), t2(G2), t2(M2), t2(V2)
+    call("psdf_adamw_multi_step", k, ctypes.addressof(nn), ctypes.addressof(a), ctypes.addressof(b_), ctypes.addressof(c_),
+         ctypes.addressof(d_), ctypes.addressof(th), 0.9, 0.99, 1e-15, step, 2, 0.5, 1)
+    for i in range(k):
+        assert torch.equal(P2[i], Pa[i]) and torch.equal(M2[i], Ma[i]) and torch.equal(V2[i], Va[i])
     # ---- schedule scalars == map_range_val on a float32 device iteration
     from permuto_sdf_b200.models import DeviceIter, map_range_val
     it_dev = torch.tensor(12345.0, device=dev)
