@@ -102,7 +102,8 @@ __device__ __forceinline__ void locate3(const float* e, Simplex3& s) {
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         float v = __fmul_rn(e[i], 0.25f);
-        float up = __fmul_rn(ceilf(v), 4.0f), down = __fmul_rn(floorf(v), 4.0f);
+        // ceil(v) * 4 == floor(v) * 4 + 4 unless v is an integer, where both candidates coincide with e[i] and `down` wins either way
+        const float down = __fmul_rn(floorf(v), 4.0f), up = __fadd_rn(down, 4.0f);
         s.rem0[i] = (__fsub_rn(up, e[i]) < __fsub_rn(e[i], down)) ? (int)up : (int)down;
         sum += s.rem0[i];
         s.rank[i] = 0;
@@ -144,15 +145,16 @@ __device__ __forceinline__ void bary_tangent3(const float* dcf, const Simplex3& 
 // h mod T without a division: q = umulhi(h, floor(2^32 / T)) is the quotient or one less, so one conditional subtraction finishes it
 // (exact for every 32-bit h; a power-of-two T needs no correction). `magic` = t_magic(T), computed on the host.
 inline unsigned t_magic(int T) { return T <= 1 ? 0xffffffffu : (unsigned)(0x100000000ull / (unsigned long long)(unsigned)T); }
+// The hash h = ((k0 P + k1) P + k2) P (mod 2^32) of the vertex key k_i = rem0[i] + r - 4 [rank[i] > 3 - r] is linear in the key over the
+// ring Z / 2^32: h_r = h_0 + r (P^3 + P^2 + P) - sum_i [rank[i] > 3 - r] 4 P^(3-i) with h_0 = rem0[0] P^3 + rem0[1] P^2 + rem0[2] P, so the
+// four vertices of a simplex share h_0 (3 multiply-adds) and each one costs 3 compare + subtract pairs -- same bits as the
+// multiply chain per vertex, less than half of its instructions.
 __device__ __forceinline__ unsigned vindex3(const Simplex3& s, int r, unsigned magic, unsigned T) {
-    unsigned h = 0;
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-        int key = s.rem0[i] + r;
-        if (s.rank[i] > 3 - r) key -= 4;
-        h += (unsigned)key;
-        h *= 2531011u;
-    }
+    constexpr unsigned P1 = 2531011u, P2 = P1 * P1, P3 = P2 * P1;
+    unsigned h = (unsigned)s.rem0[0] * P3 + (unsigned)s.rem0[1] * P2 + (unsigned)s.rem0[2] * P1 + (unsigned)r * (P3 + P2 + P1);
+    if (s.rank[0] > 3 - r) h -= 4u * P3;
+    if (s.rank[1] > 3 - r) h -= 4u * P2;
+    if (s.rank[2] > 3 - r) h -= 4u * P1;
     unsigned rem = h - __umulhi(h, magic) * T;
     return rem >= T ? rem - T : rem;
 }
