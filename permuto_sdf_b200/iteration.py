@@ -131,17 +131,6 @@ class DirectIteration:
         # Python control flow on the iteration (narrows the validity range of a captured graph, DeviceIter)
         curv_on = it < hp.iter_finish_reduce_curv
         lip_on = it >= hp.iter_start_reduce_curv
-        opt = tr.optimizer
-        zero_side = None
-        if getattr(opt, "defer_zero", False):
-            # data-parallel peer step: it leaves the (already reduced) gradients in place; they are cleared here, on a forked stream, while
-            # the sampling / forward kernels run -- joined before the first kernel that accumulates a gradient
-            if getattr(self, "_zero_stream", None) is None:
-                self._zero_stream = torch.cuda.Stream(device=dev)
-            zero_side = self._zero_stream
-            zero_side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(zero_side):
-                opt.flat_grad.zero_()
         if pre is None:
             pre = self.sample_uniform(ray_origins, ray_dirs)
         t_exit, does_hit, fg, jitter = pre["t_exit"], pre["does_hit"], pre["fg"], pre["jitter"]
@@ -157,8 +146,6 @@ class DirectIteration:
                 n_mean = fg.dp_mean_nr_samples = torch.div(n_sum + W // 2, W, rounding_mode="floor").to(torch.int32).clamp(min=1)
             N = fg.samples_pos.shape[0]
             if N == 0:
-                if zero_side is not None:
-                    torch.cuda.current_stream().wait_stream(zero_side)
                 return None                      # no sample at all (eager mode only): the caller takes the autograd formulation
             ws = self._workspace(N, R, dev)
             n_valid = fg.cur_nr_samples if static else None
@@ -221,8 +208,6 @@ class DirectIteration:
                  c_rgb, c_mask, float(hp.eikonal_weight), w_curv, scal[3:4], float(hp.offsurface_weight), w_lip,
                  c[0].detach(), c[1].detach(), c[2].detach(), c[3].detach(), ws["acc"], ws["loss"], ws["terms"])
             # ================= backward
-            if zero_side is not None:
-                torch.cuda.current_stream().wait_stream(zero_side)
             n_cnt = n_mean if n_mean is not None else n_valid
             scale_eik = float(hp.eikonal_weight) if n_cnt is not None else float(hp.eikonal_weight) / max(N, 1)
             g_wd = cal.weight_delta.grad if head[1] is not None else None

@@ -38,8 +38,6 @@ class FusedAdamW:
         self._clean = True              # flat_grad is known to be all zero (fresh, or just swept by the step kernel)
         self.hyper_dev = None           # [groups, 2] device copy of (lr, weight_decay), read by the kernel in device_step mode
         self._peer = None               # data-parallel peer-memory step (enable_peer_step)
-        self.defer_zero = False         # peer step: the gradient buffer is zeroed by the NEXT iteration (a forked memset beside its sampling
-                                        # phase, iteration.DirectIteration.run) instead of a serial 67 MB fill behind the step
         self._hyper_host = None
         self._hyper_cached = None
         for g, (ps, off, n, n_pad) in zip(groups, layout):
@@ -127,14 +125,11 @@ class FusedAdamW:
                  self.exp_avg[off:off + n], self.exp_avg_sq[off:off + n], float(g["lr"]), b1, b2, self.eps, float(g["weight_decay"]),
                  self.step_count, step_dev, hyper, float(grad_scale))
         pe["hp"].barrier(channel=0)                  # every owner has written its shard into every rank's parameters
-        if not self.defer_zero:
-            self.flat_grad.zero_()                   # ... and has read this rank's gradients
+        self.flat_grad.zero_()                       # ... and has read this rank's gradients
         self._clean = True
 
     def zero_grad(self, set_to_none=False):
         # the step kernel zeroes the gradients it consumed; a backward that was not followed by a step leaves them dirty
-        if self.defer_zero:
-            return                      # the iteration zeroes the buffer itself (always, as a branch beside its sampling phase)
         if not self._clean:
             self.flat_grad.zero_()
         self._clean = False             # the caller is about to run a backward

@@ -433,8 +433,6 @@ class Trainer:
             loss = self._direct.run(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal, pre=pre)
             if loss is not None:
                 return loss
-        elif getattr(self.optimizer, "defer_zero", False):
-            self.optimizer.flat_grad.zero_()
         loss = self.losses(ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, iter_nr_for_anneal)
         loss.backward()
         return loss.detach()
@@ -514,7 +512,6 @@ class Trainer:
             # no all-reduce at all: one fused reduce + AdamW + broadcast kernel per parameter group over NVLink peer memory
             # (optim.FusedAdamW.enable_peer_step, csrc/optim.cu k_adamw_dp); the step runs eagerly behind the replayed iteration graph
             self.optimizer.enable_peer_step()
-            self.optimizer.defer_zero = self._direct is not None     # the iteration clears the gradient buffer beside its sampling phase
             self._dp = dict(world=int(world), mode="peer", work=None, dist=dist)
             if getattr(self.model_sdf, "fused", None) is not None:
                 self.model_sdf.fused.repack()
