@@ -383,12 +383,6 @@ int psdf_adamw_dp_step(long long n, long long shard_lo, int world, int rank, con
                        uint64_t mc_grad_ptr, uint64_t mc_param_ptr, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
                        float eps, float weight_decay, int step, const int* step_dev, const float* hyper_dev, float grad_scale, void* stream);
 
-/* self-test of the tensor-core path: D[128,N] = A[128,K] * B[N,K]^T (N,K <= 64) */
-int psdf_debug_umma_gemm(int N, int K, const float* A, const float* B, float* D, void* stream);
-/* self-test of the weight-gradient product: D[M,N] = A[128,M]^T * B[128,N] (M,N <= 64) with the sample axis as the MMA K
- * dimension and MN-major operands; dump [128,64] = every TMEM lane x column of the accumulator region */
-int psdf_debug_umma_gemm_tn(int M, int N, const float* A, const float* B, float* dump, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -15,13 +15,26 @@ def rel(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
+def _probe_call(name, *args):
+    """tcgen05 self tests live in the probe library (tests/probe/libumma_probe.so, test infrastructure), not in the product ABI"""
+    import ctypes
+    import os
+    so = os.path.join(os.path.dirname(os.path.abspath(__file__)), "probe", "libumma_probe.so")
+    lib = ctypes.CDLL(so)
+    conv = [a.data_ptr() if isinstance(a, torch.Tensor) else int(a) for a in args] + [torch.cuda.current_stream().cuda_stream]
+    fn = getattr(lib, name)
+    fn.argtypes = [ctypes.c_int if isinstance(a, int) else ctypes.c_void_p for a in args] + [ctypes.c_void_p]
+    rc = fn(*conv)
+    assert rc == 0, "%s failed with %d" % (name, rc)
+
+
 def _gemm_err(N, K):
     from permuto_sdf_b200 import call
     torch.manual_seed(N * 100 + K)
     A = torch.randn(128, K, device="cuda")
     B = torch.randn(N, K, device="cuda")
     D = torch.zeros(128, N, device="cuda")
-    call("psdf_debug_umma_gemm", N, K, A, B, D)
+    _probe_call("umma_probe_gemm", N, K, A, B, D)
     torch.cuda.synchronize()
     return rel(D, A.double() @ B.double().t())
 
@@ -33,7 +46,7 @@ def test_umma_gemm_self_test(cuda, N, K):
     A = torch.randn(128, K, device="cuda")
     B = torch.randn(N, K, device="cuda")
     D = torch.zeros(128, N, device="cuda")
-    call("psdf_debug_umma_gemm", N, K, A, B, D)
+    _probe_call("umma_probe_gemm", N, K, A, B, D)
     torch.cuda.synchronize()
     ref = (A.double() @ B.double().t())
     err = rel(D, ref)
@@ -137,7 +150,7 @@ def test_umma_transposed_gemm_weight_gradient_layout(cuda, M, N):
     A = torch.randn(128, M, device="cuda")
     B = torch.randn(128, N, device="cuda")
     dump = torch.full((128, 64), float("nan"), device="cuda")
-    call("psdf_debug_umma_gemm_tn", M, N, A, B, dump)
+    _probe_call("umma_probe_gemm_tn", M, N, A, B, dump)
     torch.cuda.synchronize()
     want = (A.double().t() @ B.double()).float()
     Mp = (M + 15) // 16 * 16
