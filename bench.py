@@ -179,6 +179,7 @@ def run_ours(args):
     tr.set_analytic_scene()
     tr.iter_nr = 20000          # past coarse-to-fine: all 16 levels active, cos-anneal half way
     graphed = not (args.modular or args.eager)
+    graphed_mode = graphed
     if graphed:
         tr.enable_cuda_graph(warmup_steps=3)
     H, W, f = 600, 800, 1000.0
@@ -206,7 +207,10 @@ def run_ours(args):
         dp = tr._dp is not None
         # device-resident indices were materialised before the synchronize() that precedes the timed region (inputs_ready): the
         # parameter-free head of the iteration may then start beside the previous optimizer step
-        loss = tr.step_from_reel(reel, pix, img, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1 or dp), inputs_ready=not e2e)
+        # e2e: the loss is read through Trainer's HostLoss handle (device -> pinned host copy queued right behind the forward/backward
+        # graph): float(loss) below waits for that copy, not for the optimizer step, so the host launches the next step's head beside it
+        loss = tr.step_from_reel(reel, pix, img, update_occupancy=(i % 8 == 0), optimizer_step=(world == 1 or dp), inputs_ready=not e2e,
+                                 loss_to_host=e2e and graphed_mode)
         if world > 1 and not dp:
             # legacy path (PSDF_DP_MODE=legacy): one blocking NCCL all-reduce of the flat gradient buffer between the two graphs
             dist.all_reduce(tr.optimizer.flat_grad if flat is None else flat.flat, op=dist.ReduceOp.SUM)

@@ -314,6 +314,26 @@ def run_net_in_chunks(ray_origins_full, ray_dirs_full, chunk_size, with_mask, hy
     return torch.cat(rgb_l, 0), (torch.cat(bg_l, 0) if bg_l else None), torch.cat(nrm_l, 0), torch.cat(ws_l, 0)
 
 
+class HostLoss:
+    """Loss of an iteration on its way to the host: the 4-byte device -> pinned-host copy is queued right behind the iteration's
+    forward/backward graph (BEFORE its optimizer step), float() / item() wait for that copy only. The host can therefore read the
+    loss of iteration i and launch iteration i+1 while the optimizer step of iteration i is still running (Trainer.step_from_reel
+    with loss_to_host=True). Valid until the next step of the same Trainer."""
+
+    def __init__(self, host, event, dev):
+        self.host, self.event, self.dev = host, event, dev
+
+    def __float__(self):
+        self.event.synchronize()
+        return float(self.host[0])
+
+    def item(self):
+        return float(self)
+
+    def detach(self):
+        return self.dev
+
+
 class Trainer:
     """State of one PermutoSDF training run on synthetic data (models, occupancy grid, optimizer) and the
     per-iteration step of train_permuto_sdf.py:311-422 (after sphere init), with `--with_mask` semantics."""
@@ -675,7 +695,8 @@ class Trainer:
             cg["it_dev"].fill_(float(self.iter_nr))
             cg["it_host"] = self.iter_nr
 
-    def step_from_reel(self, tensor_reel, pixel_indices, image_indices, update_occupancy=None, optimizer_step=True, inputs_ready=False):
+    def step_from_reel(self, tensor_reel, pixel_indices, image_indices, update_occupancy=None, optimizer_step=True, inputs_ready=False,
+                       loss_to_host=False):
         """one iteration from (pixel, image) indices into a TensorReel: ray generation (PermutoSDF.rays_from_reel_indices) + step.
         Under CUDA-graph replay the indices are the graph's inputs -- host (pinned) or device int32 tensors, copied straight into the
         static buffers -- and the ray-generation kernel is part of the replayed graph."""
@@ -687,10 +708,10 @@ class Trainer:
             return self.step(o, d, gt, gm, idx, update_occupancy=update_occupancy, optimizer_step=optimizer_step)
         self.model_sdf.train(); self.model_rgb.train()
         return self._step_graphed(pixel_indices, image_indices, None, None, None, update_occupancy, optimizer_step, make_rays=make_rays,
-                                  inputs_ready=inputs_ready)
+                                  inputs_ready=inputs_ready, loss_to_host=loss_to_host)
 
     def _step_graphed(self, ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices, update_occupancy, optimizer_step, make_rays=None,
-                      inputs_ready=False):
+                      inputs_ready=False, loss_to_host=False):
         cg = self._cg
         it = self.iter_nr
         self._sync_device_iter()
@@ -749,6 +770,13 @@ class Trainer:
             for m in (self.model_sdf, self.model_rgb, self.model_bg):
                 if m is not None:
                     m.last_iter_nr = it
+        if loss_to_host:
+            # 4-byte copy + event right behind the forward/backward graph: the host reads the loss without waiting for the optimizer step
+            if cg.get("loss_host") is None:
+                cg["loss_host"], cg["ev_loss"] = torch.zeros(1).pin_memory(), torch.cuda.Event()
+            cg["loss_host"].copy_(loss.detach().reshape(1), non_blocking=True)
+            cg["ev_loss"].record(torch.cuda.current_stream())
+            loss = HostLoss(cg["loss_host"], cg["ev_loss"], loss)
         if update_occupancy is None:
             update_occupancy = (it % 8 == 0)
         if update_occupancy and self.hp.use_occupancy_grid:

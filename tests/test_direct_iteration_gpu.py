@@ -112,7 +112,9 @@ def test_direct_iteration_trains_under_graph_replay(cuda):
     for i in range(8):
         pix = torch.randint(0, 60 * 80, (256,), generator=gen, dtype=torch.int32).cuda()
         img = torch.randint(0, 4, (256,), generator=gen, dtype=torch.int32).cuda()
-        losses.append(float(tr.step_from_reel(reel, pix, img)))
+        h = tr.step_from_reel(reel, pix.cpu().pin_memory() if i % 2 else pix, img.cpu().pin_memory() if i % 2 else img, loss_to_host=True)
+        losses.append(float(h))                       # waits for the 4-byte copy behind the forward/backward graph only
+        assert losses[-1] == float(h.detach()), "host copy of the loss differs from the device value"
     launches = tr.graph_launches_per_step()
     step_dev, it_dev = int(tr.optimizer.step_dev), float(tr._cg["it_dev"])
     tr.disable_cuda_graph()
