@@ -39,6 +39,7 @@ class DirectIteration:
         self.tr = trainer
         self._ws = None
         self._ws_key = None
+        self._fixed = None
         self._scal_params = None
 
     # ------------------------------------------------------------------------------------------ applicability
@@ -60,6 +61,23 @@ class DirectIteration:
         return None
 
     # ------------------------------------------------------------------------------------------ persistent buffers
+    def _fixed_workspace(self, dev):
+        """buffers whose size does not depend on the sample count (used by the part of the iteration that runs beside the sampling)"""
+        if self._fixed is not None and self._fixed["dev"] == str(dev):
+            return self._fixed
+        fr = self.tr.model_rgb.fused
+        dims = [fr.in_dim] + fr.h + [3]
+        sizes = [dims[l + 1] * dims[l] for l in range(4)]
+        gweff = torch.zeros(sum(sizes), device=dev)          # d loss / d W_eff: accumulated by k_rgb_fused_backward (per-tile reductions), reset by psdf_lipschitz_backward4
+        offs = [0, sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]]
+        f = lambda *s: torch.empty(*s, device=dev)
+        self._fixed = dict(dev=str(dev), off_pts=f(self.N_OFF, 3), sdf_off=f(self.N_OFF, 1), g_off=f(self.N_OFF, 1),
+                           acc=torch.zeros(8, device=dev), loss=torch.zeros(1, device=dev), terms=torch.zeros(12, device=dev),
+                           scal=torch.zeros(8, device=dev),
+                           gweff=[gweff[offs[l]:offs[l] + sizes[l]].view(dims[l + 1], dims[l]) for l in range(4)],
+                           stream=torch.cuda.Stream(device=dev))
+        return self._fixed
+
     def _workspace(self, N, R, dev):
         key = (N, R, str(dev))
         if self._ws_key == key:
@@ -69,19 +87,12 @@ class DirectIteration:
         f = lambda *s: torch.empty(*s, device=dev)
         from ._lib import load_library
         lib = load_library()
-        dims = [fr.in_dim] + fr.h + [3]
-        sizes = [dims[l + 1] * dims[l] for l in range(4)]
-        gweff = torch.zeros(sum(sizes), device=dev)          # d loss / d W_eff: accumulated by k_rgb_fused_backward (per-tile reductions), reset by psdf_lipschitz_backward4
-        offs = [0, sizes[0], sizes[0] + sizes[1], sizes[0] + sizes[1] + sizes[2]]
-        ws = dict(
+        ws = dict(self._fixed_workspace(dev))
+        ws.update(
             sdf=f(N, 1), grad=f(N, 3), geom=f(N, fs.out_dim - 1), x_raw=f(N, 3),
             shifted=f(N, 3), sdf_s=f(N, 1), grad_s=f(N, 3),
-            off_pts=f(self.N_OFF, 3), sdf_off=f(self.N_OFF, 1), g_off=f(self.N_OFF, 1),
             alpha=f(N), T=f(N), pred=f(R, 3), wsum=f(R, 1), bgT=f(R, 1), ray_loss=f(R, 3),
             g_sdf=f(N, 1), g_grad=f(N, 3), g_x=f(N, 3), g_grad_s=f(N, 3), g_geom=f(N, fs.out_dim - 1),
-            acc=torch.zeros(8, device=dev), loss=torch.zeros(1, device=dev), terms=torch.zeros(12, device=dev),
-            scal=torch.zeros(8, device=dev),
-            gweff=[gweff[offs[l]:offs[l] + sizes[l]].view(dims[l + 1], dims[l]) for l in range(4)],
             rgb_ws=torch.empty(int(lib.psdf_rgb_fused_backward_workspace_bytes(N)), dtype=torch.uint8, device=dev),
             sdf_ws=torch.empty(int(lib.psdf_sdf_fused_backward_multi_workspace_bytes(N, N, self.N_OFF)), dtype=torch.uint8, device=dev),
         )
@@ -134,7 +145,22 @@ class DirectIteration:
         if pre is None:
             pre = self.sample_uniform(ray_origins, ray_dirs)
         t_exit, does_hit, fg, jitter = pre["t_exit"], pre["does_hit"], pre["fg"], pre["jitter"]
+        n_off = self.N_OFF
+        L = fr.layers
+        c = m_rgb.mlp.lipshitz_bound_per_layer
         with torch.no_grad():
+            # ---------------- what does not depend on the samples runs on a forked stream beside the importance-sampling chain (a parallel
+            # branch of the captured graph): schedule scalars, off-surface points, Lipschitz normalisation + packing of the colour weights
+            fx = self._fixed_workspace(dev)
+            cur, side = torch.cuda.current_stream(), fx["stream"]
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                scal = self._scalars(it, fx)
+                u01 = tr.draw("offsurface_u01", lambda: torch.rand(3, n_off, device=dev))
+                call("psdf_sphere_rand_points_inside_u01", n_off, tr.aabb.m_radius, u01, fx["off_pts"])
+                call("psdf_lipschitz_pack4", fr.in_dim, *fr.h, 3, L[0].weight.detach(), L[0].bias.detach(), c[0].detach(), L[1].weight.detach(),
+                     L[1].bias.detach(), c[1].detach(), L[2].weight.detach(), L[2].bias.detach(), c[2].detach(), L[3].weight.detach(),
+                     L[3].bias.detach(), c[3].detach(), fr.blob)
             if fg.samples_pos.shape[0] != 0:
                 fg = importance_sampling_sdf_model(m_sdf, fg, ray_origins, ray_dirs, t_exit, it, hp.nr_samples_imp_sampling, jitter=jitter)
             n_mean = None
@@ -144,12 +170,12 @@ class DirectIteration:
                 dist.all_reduce(n_sum, op=dist.ReduceOp.SUM)
                 W = int(hp.dp_world)
                 n_mean = fg.dp_mean_nr_samples = torch.div(n_sum + W // 2, W, rounding_mode="floor").to(torch.int32).clamp(min=1)
+            cur.wait_stream(side)                # join the forked branch
             N = fg.samples_pos.shape[0]
             if N == 0:
                 return None                      # no sample at all (eager mode only): the caller takes the autograd formulation
             ws = self._workspace(N, R, dev)
             n_valid = fg.cur_nr_samples if static else None
-            scal = self._scalars(it, ws)
             cos_dev, inv_s = scal[0:1], scal[1:2]
             m_rgb.volume_renderer_neus.last_inv_s = scal[2:3]
             m_rgb.volume_renderer_neus.deviation_network.last_variance = None
@@ -159,20 +185,12 @@ class DirectIteration:
             enc = m_sdf.encoding
             m_sdf.last_iter_nr = int(it)
             win = m_sdf.window(it).view(-1).contiguous()
-            n_off = self.N_OFF
-            u01 = tr.draw("offsurface_u01", lambda: torch.rand(3, n_off, device=dev))
-            call("psdf_sphere_rand_points_inside_u01", n_off, tr.aabb.m_radius, u01, ws["off_pts"])
             pos = fg.samples_pos
             sdf_args = (enc.nr_levels, enc.capacity, enc.lattice_values.detach(), enc.scale_factor, enc.shift_tensor(), win,
                         enc.concat_points_scaling, fs.hidden, fs.out_dim, fs.blob)
             call("psdf_sdf_fused_forward_multi", *sdf_args, N, pos, ws["sdf"], ws["grad"], ws["geom"], n_off, ws["off_pts"], ws["sdf_off"],
                  None, None)
-            # ---------------- colour network
-            L = fr.layers
-            c = m_rgb.mlp.lipshitz_bound_per_layer
-            call("psdf_lipschitz_pack4", fr.in_dim, *fr.h, 3, L[0].weight.detach(), L[0].bias.detach(), c[0].detach(), L[1].weight.detach(),
-                 L[1].bias.detach(), c[1].detach(), L[2].weight.detach(), L[2].bias.detach(), c[2].detach(), L[3].weight.detach(),
-                 L[3].bias.detach(), c[3].detach(), fr.blob)
+            # ---------------- colour network (weights normalised + packed on the forked branch)
             enc_c = m_rgb.encoding
             win_c = fr._window(it)
             rgb_args = (N, enc_c.nr_levels, enc_c.capacity, pos, fg.samples_dirs, ws["grad"], ws["geom"], ws["geom"].shape[1],

@@ -547,7 +547,7 @@ class VolumeRendering:
         imp = RaySamplesPacked(R, R * k, zero_count=False)
         imp.rays_have_equal_nr_of_samples = True
         imp.fixed_nr_of_samples_per_ray = k
-        cdf = torch.zeros(VolumeRendering._N(rsp), 1, device=rsp.samples_z.device)
+        cdf = torch.empty(VolumeRendering._N(rsp), 1, device=rsp.samples_z.device)      # scratch: every entry is written before it is read
         call("psdf_vr_importance_round", *rsp._rsp(), _f32(ray_origins, "ray_origins", 3), _f32(ray_dirs, "ray_dirs", 3), rsp.ray_fixed_dt,
              rsp.samples_dt, rsp.samples_z, _f32(sdf_samples, "sdf").reshape(-1, 1), float(inv_s), 1 if dynamic_inv_s else 0,
              float(inv_s_multiplier), k, *VolumeRendering.m_rng.args(), 1 if jitter_samples else 0, cdf, imp.samples_pos, imp.samples_dirs,
