@@ -492,7 +492,9 @@ def cpu_baseline(sample_rays, steps, warmup, threads=None):
     from oracle.cpu_step import time_cpu_step
     threads = threads or min(os.cpu_count() or 1, 32)      # the 65-sample-per-ray port does not scale past a few dozen threads
     med, ts = time_cpu_step(sample_rays, SAMPLES_PER_RAY, steps, warmup, threads)
-    return {"value": sample_rays / med, "unit": "rays/s", "cores": threads, "kind": "port",
+    return {"value": sample_rays / med, "unit": "rays/s", "cores": threads, "cores_available": os.cpu_count(),
+            "threads_note": "the port's per-step work (tens of samples per thread) stops scaling past ~32 threads; more threads measured slower",
+            "kind": "port",
             "sample": "%d rays x %d samples per step, %d steps, median; SDF encoding + 3x64 MLP forward, d sdf/dx, eikonal + feature loss, backward "
                       "(double backward); the reference has no CPU path, this is the oracle restatement" % (sample_rays, SAMPLES_PER_RAY, steps),
             "seconds_per_step": med}
