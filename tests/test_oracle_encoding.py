@@ -133,3 +133,27 @@ def test_coarse2fine_window():
     from permutohedral_encoding import Coarse2Fine
     c = Coarse2Fine(16)
     assert torch.allclose(c(0.3).cpu(), w) and c.get_last_t() == 0.3
+
+
+def test_vertex_hash_is_linear_in_the_key():
+    """The fused kernels hash the four vertices of a simplex from one shared h_0 (csrc/fused_common.cuh vindex3):
+    h = ((k0 P + k1) P + k2) P (mod 2^32) with k_i = rem0[i] + r - 4 [rank[i] > 3 - r] equals
+    rem0 . (P^3, P^2, P) + r (P^3 + P^2 + P) - 4 sum_i [rank[i] > 3 - r] P^(3-i) over Z / 2^32. Checked here on random keys."""
+    import random
+    rnd = random.Random(7)
+    P, M = 2531011, 2 ** 32
+    P1, P2, P3 = P, P * P % M, P * P * P % M
+    for _ in range(20000):
+        rem = [rnd.randint(-2 ** 24, 2 ** 24) for _ in range(3)]
+        rank = rnd.sample(range(4), 4)
+        for r in range(4):
+            h = 0
+            for i in range(3):
+                key = rem[i] + r - (4 if rank[i] > 3 - r else 0)
+                h = (h + key) % M
+                h = h * P % M
+            g = (rem[0] * P3 + rem[1] * P2 + rem[2] * P1 + r * (P3 + P2 + P1)) % M
+            for i, q in enumerate((P3, P2, P1)):
+                if rank[i] > 3 - r:
+                    g = (g - 4 * q) % M
+            assert g == h

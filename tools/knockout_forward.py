@@ -30,11 +30,10 @@ def t(fn, n=30):
 with torch.no_grad():
     print("%%.1f" %% t(lambda: f(pos, 20000, with_gradient=True)))
 ''' % (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "compat"))
-NAMES = {63: "barriers only (sync skeleton)", 127: "skeleton, mbarrier.arrive instead of tcgen05.commit", 255: "skeleton, plain arrive, no fence.proxy.async",
+NAMES = {0: "everything", 1: "no encoder", 2: "no MMA", 4: "no GELU", 8: "no operand stores", 12: "no GELU, no stores",
+         14: "no MMA, GELU, stores", 16: "no TMEM loads", 32: "no output stores", 15: "TMEM loads + barriers + outputs",
+         63: "barriers only (sync skeleton)", 127: "skeleton, mbarrier.arrive instead of tcgen05.commit",
          191: "skeleton, no fence.proxy.async", 128: "everything but fence.proxy.async (wrong results)"}
-NAMES_OLD = {0: "everything", 1: "no encoder", 2: "no MMA", 4: "no GELU", 8: "no operand stores", 12: "no GELU, no stores", 14: "no MMA, GELU, stores",
-         15: "TMEM loads + barriers + outputs", 31: "barriers + outputs", 47: "TMEM loads + barriers", 63: "barriers only (sync skeleton)",
-         16: "no TMEM loads", 32: "no output stores"}
 for k, name in NAMES.items():
     env = dict(os.environ, PSDF_EXPERIMENT_KNOCKOUT=str(k))
     out = subprocess.run([sys.executable, "-c", CODE], env=env, capture_output=True, text=True)
