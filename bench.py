@@ -460,8 +460,8 @@ def run_sphere_trace(args):
         dist.destroy_process_group()
 
 
-NCU_KERNEL_OF = {"psdf_sdf_fused_forward": "k_sdf_fused<1>", "psdf_sdf_fused_backward": "k_sdf_fused_backward",
-                 "psdf_sdf_fused_forward_multi": "k_sdf_fused<1>", "psdf_sdf_fused_backward_multi": "k_sdf_fused_backward",
+NCU_KERNEL_OF = {"psdf_sdf_fused_forward": "k_sdf_fused_dual", "psdf_sdf_fused_backward": "k_sdf_fused_backward",
+                 "psdf_sdf_fused_forward_multi": "k_sdf_fused_dual", "psdf_sdf_fused_backward_multi": "k_sdf_fused_backward",
                  "psdf_rgb_fused_forward": "k_rgb_fused", "psdf_rgb_fused_backward": "k_rgb_fused_backward",
                  "psdf_sdf_sphere_trace": "k_sdf_sphere_trace"}
 
