@@ -289,6 +289,7 @@ def run_ours(args):
         "psdf_sdf_fused_backward_multi": 12 + 2 * L * 4 * 8 + 4 + 12 + 128,
         "psdf_rgb_fused_forward": 12 + L * 4 * 8 + 12 + 12 + 128 + 12,
         "psdf_rgb_fused_backward": 12 + 2 * L * 4 * 8 + 12 + 12 + 128 + 12 + 12 + 128,
+        "psdf_rgb_fused_backward_acc": 12 + 2 * L * 4 * 8 + 12 + 12 + 128 + 12 + 12 + 128,
     }
     units = dict(_lib.LAST_UNITS)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the tracked `ncu --set full` capture of this workload
@@ -463,6 +464,7 @@ def run_sphere_trace(args):
 NCU_KERNEL_OF = {"psdf_sdf_fused_forward": "k_sdf_fused_dual", "psdf_sdf_fused_backward": "k_sdf_fused_backward",
                  "psdf_sdf_fused_forward_multi": "k_sdf_fused_dual", "psdf_sdf_fused_backward_multi": "k_sdf_fused_backward",
                  "psdf_rgb_fused_forward": "k_rgb_fused", "psdf_rgb_fused_backward": "k_rgb_fused_backward",
+                 "psdf_rgb_fused_backward_acc": "k_rgb_fused_backward",
                  "psdf_sdf_sphere_trace": "k_sdf_sphere_trace"}
 
 
