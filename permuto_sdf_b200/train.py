@@ -714,13 +714,16 @@ class Trainer:
                       inputs_ready=False, loss_to_host=False):
         cg = self._cg
         it = self.iter_nr
-        if self._dp is not None and cg.get("ev_fb") is not None:
-            # data-parallel runs: keep the host at most one iteration ahead of the GPU (wait for the END OF THE PREVIOUS forward/backward
-            # graph; its optimizer step may still be running). Measured on 2 B200s (profiles/README.md): with the host free to queue many
-            # iterations of graph replays + eagerly launched cross-rank barrier / peer-step kernels on two streams, the step time was
-            # 1.34 ms in two runs and 1.69 / 3.19 ms in two others, while the end-to-end path -- which reads the loss every step and so
-            # never runs ahead -- gave 1.30-1.33 ms in every run. The wait costs nothing when the GPU is the bottleneck.
-            cg["ev_fb"].synchronize()
+        if self._dp is not None:
+            # data-parallel runs: keep the host at most TWO iterations ahead of the GPU (wait for the end of the forward/backward graph of
+            # the iteration before the previous one). Measured on 2 B200s (profiles/README.md): with the host free to queue many iterations
+            # of graph replays + eagerly launched cross-rank barrier / peer-step kernels on two streams, the step time was 1.34 ms in two
+            # runs and 1.69 / 3.19 ms in two others (and the NVML sampler thread of the slow runs got a third of its time slices: the
+            # process was spinning), while the end-to-end path -- which reads the loss every step and so never runs ahead -- gave
+            # 1.30-1.33 ms in every run. Two iterations of queued work keep the GPU fed; the wait costs nothing then.
+            hist = cg.setdefault("ev_hist", [])
+            if len(hist) >= 2:
+                hist[-2].synchronize()
         self._sync_device_iter()
         # with make_rays the graph inputs are (pixel indices, image indices) and ray generation is captured with the iteration
         inputs = [ray_origins, ray_dirs] if make_rays is not None else [ray_origins, ray_dirs, gt_rgb, gt_mask, img_indices]
@@ -794,6 +797,12 @@ class Trainer:
             ev = cg["ev_fb"] if cg["ev_fb"] is not None else torch.cuda.Event()
             ev.record(torch.cuda.current_stream())          # forward/backward (+ occupancy refresh) of this iteration are queued up to here
             cg["ev_fb"] = ev
+        if self._dp is not None:
+            e = torch.cuda.Event()
+            e.record(torch.cuda.current_stream())
+            hist = cg.setdefault("ev_hist", [])
+            hist.append(e)
+            del hist[:-3]
         self.apply_schedules(it)
         if optimizer_step:
             self.optimizer_step()
