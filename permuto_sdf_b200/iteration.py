@@ -28,7 +28,7 @@ import ctypes
 import torch
 
 from ._lib import call
-from .models import DeviceIter, map_range_val
+from .models import DeviceIter
 from .permuto_sdf import RaySamplesPacked
 
 
